@@ -1,0 +1,748 @@
+// icp_sweep.cu -- batched cluster-ICP sweep for sm_100a (B200).
+//
+// Replaces masked_icp() (AutoURDF PointCloud/cluster_icp.py:118-191) and the open3d
+// registration_icp() call inside it (:157-159), for B (frame, cluster) tiles per call.
+//
+// Kernels (all on the caller's stream, no host synchronisation):
+//   1. box_count_kernel   one CTA per tile: AABB of the predicted cluster (:133-140),
+//                         count of frame points strictly inside it (:142-146)
+//   2. tile_scan_kernel   exclusive scan of the (even-padded) counts -> compacted offsets,
+//                         capacity check
+//   3. mask_fill_kernel   order-preserving compaction of the masked target points into
+//                         float64 SoA (x|y|z) + original index (:148)
+//   4. icp_tiles_kernel   one CTA per tile, persistent to convergence: target chunk staged
+//                         in shared memory by the TMA engine (cp.async.bulk + mbarrier),
+//                         brute-force squared-L2 argmin in float64 with the reference's
+//                         operation order, warp-shuffle reductions, 3x3 Jacobi SVD pose fit,
+//                         SE(3) compose/apply, open3d's convergence rule.
+//
+// Compile with -fmad=false: distances and point transforms must round exactly like the
+// float64 CPU reference (no FMA contraction), otherwise near-tie correspondences flip.
+#include <math.h>
+#include <stdio.h>
+
+#include "common.cuh"
+
+namespace aurdf {
+
+constexpr int kIcpThreads = 128;
+constexpr int kIcpWarps = kIcpThreads / 32;
+constexpr int kQChunk = 512;      // target points staged per shared-memory chunk (12 KB as f64 SoA)
+constexpr int kPSmemMax = 2048;   // most source points a tile may keep in shared memory
+constexpr int kNumSums = 17;      // count, err2, sum p (3), sum q (3), sum q p^T (9)
+
+struct WsLayout {
+    size_t box, cnt, toff, qx, qy, qz, qi, pspill, status, total;
+};
+
+static WsLayout make_layout(int64_t B, int64_t total_src, int64_t cap) {
+    WsLayout L;
+    size_t o = 0;
+    auto take = [&](size_t bytes) {
+        size_t r = o;
+        o = align_up(o + bytes, 256);
+        return r;
+    };
+    L.box = take((size_t)B * 6 * sizeof(double));
+    L.cnt = take((size_t)B * sizeof(int));
+    L.toff = take((size_t)(B + 1) * sizeof(long long));
+    L.status = take(4 * sizeof(int));
+    L.qx = take((size_t)cap * sizeof(double));
+    L.qy = take((size_t)cap * sizeof(double));
+    L.qz = take((size_t)cap * sizeof(double));
+    L.qi = take((size_t)cap * sizeof(int));
+    L.pspill = take((size_t)total_src * 3 * sizeof(double));
+    L.total = o;
+    return L;
+}
+
+// ------------------------------------------------------------------------------------------
+// 1. AABB + count
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool inside_box(double x, double y, double z, const double *bx) {
+    return x > bx[0] && x < bx[3] && y > bx[1] && y < bx[4] && z > bx[2] && z < bx[5];
+}
+
+__global__ void __launch_bounds__(kIcpThreads)
+box_count_kernel(const void *__restrict__ box_xyz, int box_dtype, const int *__restrict__ box_off,
+                 const void *__restrict__ tgt_xyz, int pts_dtype, const int *__restrict__ tgt_off,
+                 const int *__restrict__ tile_frame, double box_scale, double *__restrict__ box_out,
+                 int *__restrict__ cnt_out) {
+    __shared__ double s_mm[kIcpWarps][6];
+    __shared__ double s_box[6];
+    __shared__ int s_cnt[kIcpWarps];
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool no_mask = box_xyz == nullptr;  // plain registration_icp: every frame point is a target
+    const int b0 = no_mask ? 0 : box_off[b], nb = no_mask ? 0 : box_off[b + 1] - b0;
+
+    double lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (int i = tid; i < nb; i += kIcpThreads) {
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            double v = ld_coord(box_xyz, box_dtype, 3 * (size_t)(b0 + i) + d);
+            lo[d] = fmin(lo[d], v);
+            hi[d] = fmax(hi[d], v);
+        }
+    }
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo[d] = fmin(lo[d], __shfl_xor_sync(0xffffffffu, lo[d], o));
+            hi[d] = fmax(hi[d], __shfl_xor_sync(0xffffffffu, hi[d], o));
+        }
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            s_mm[warp][d] = lo[d];
+            s_mm[warp][3 + d] = hi[d];
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        for (int d = 0; d < 3; ++d) {
+            double l = s_mm[0][d], h = s_mm[0][3 + d];
+            for (int w = 1; w < kIcpWarps; ++w) {
+                l = fmin(l, s_mm[w][d]);
+                h = fmax(h, s_mm[w][3 + d]);
+            }
+            double blo, bhi;
+            if (no_mask) {
+                blo = -INFINITY;
+                bhi = INFINITY;
+            } else if (nb <= 0) {
+                blo = INFINITY;
+                bhi = -INFINITY;
+            } else if (box_dtype == AURDF_F32) {
+                // numpy keeps float32 through np.mean / python-scalar multiply (cluster_icp.py:138-140)
+                float lf = (float)l, hf = (float)h;
+                float c = __fmul_rn(__fadd_rn(lf, hf), 0.5f);
+                float size = __fsub_rn(hf, lf);
+                float hs = __fmul_rn((float)(0.5 * box_scale), size);
+                blo = (double)__fsub_rn(c, hs);
+                bhi = (double)__fadd_rn(c, hs);
+            } else {
+                double c = __dmul_rn(__dadd_rn(l, h), 0.5);
+                double size = __dsub_rn(h, l);
+                double hs = __dmul_rn(0.5 * box_scale, size);
+                blo = __dsub_rn(c, hs);
+                bhi = __dadd_rn(c, hs);
+            }
+            s_box[d] = blo;
+            s_box[3 + d] = bhi;
+            box_out[6 * (size_t)b + d] = blo;
+            box_out[6 * (size_t)b + 3 + d] = bhi;
+        }
+    }
+    __syncthreads();
+    const int f = tile_frame[b];
+    const int t0 = tgt_off[f], M = tgt_off[f + 1] - t0;
+    int c = 0;
+    for (int i = tid; i < M; i += kIcpThreads) {
+        const size_t e = 3 * (size_t)(t0 + i);
+        double x = ld_coord(tgt_xyz, pts_dtype, e), y = ld_coord(tgt_xyz, pts_dtype, e + 1),
+               z = ld_coord(tgt_xyz, pts_dtype, e + 2);
+        c += inside_box(x, y, z, s_box) ? 1 : 0;
+    }
+    c = warp_sum_int(c);
+    if (lane == 0) s_cnt[warp] = c;
+    __syncthreads();
+    if (tid == 0) {
+        int t = 0;
+        for (int w = 0; w < kIcpWarps; ++w) t += s_cnt[w];
+        cnt_out[b] = t;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// 2. scan of even-padded counts (single CTA; B is at most a few 10^5)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024)
+tile_scan_kernel(const int *__restrict__ cnt, int B, long long capacity, long long *__restrict__ toff,
+                 int *__restrict__ status_int, int *__restrict__ status_user) {
+    __shared__ long long s_warp[32];
+    __shared__ long long s_carry;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_carry = 0;
+    __syncthreads();
+    for (int base = 0; base < B; base += 1024) {
+        int i = base + tid;
+        long long v = (i < B) ? (long long)((cnt[i] + 1) & ~1) : 0;
+        long long inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            long long n = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += n;
+        }
+        if (lane == 31) s_warp[warp] = inc;
+        __syncthreads();
+        if (warp == 0) {
+            long long w = s_warp[lane];
+            long long winc = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                long long n = __shfl_up_sync(0xffffffffu, winc, o);
+                if (lane >= o) winc += n;
+            }
+            s_warp[lane] = winc - w;  // exclusive
+        }
+        __syncthreads();
+        long long excl = s_carry + s_warp[warp] + inc - v;
+        if (i < B) toff[i] = excl;
+        __syncthreads();
+        if (tid == 1023) s_carry = excl + v;
+        __syncthreads();
+    }
+    if (tid == 0) {
+        long long total = s_carry;
+        toff[B] = total;
+        int over = total > capacity ? 1 : 0;
+        status_int[0] = over;
+        status_int[1] = (int)(total & 0xffffffffLL);
+        status_int[2] = (int)(total >> 32);
+        if (status_user) {
+            status_user[0] = over;
+            status_user[1] = status_int[1];
+            status_user[2] = status_int[2];
+            status_user[3] = 0;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// 3. order-preserving compaction of the masked target points
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kIcpThreads)
+mask_fill_kernel(const void *__restrict__ tgt_xyz, int pts_dtype, const int *__restrict__ tgt_off,
+                 const int *__restrict__ tile_frame, const double *__restrict__ box,
+                 const long long *__restrict__ toff, const int *__restrict__ status_int,
+                 double *__restrict__ qx, double *__restrict__ qy, double *__restrict__ qz,
+                 int *__restrict__ qi) {
+    if (status_int[0]) return;
+    __shared__ double s_box[6];
+    __shared__ int s_wcnt[kIcpWarps];
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid < 6) s_box[tid] = box[6 * (size_t)b + tid];
+    __syncthreads();
+    const int f = tile_frame[b];
+    const int t0 = tgt_off[f], M = tgt_off[f + 1] - t0;
+    const long long base = toff[b];
+    int running = 0;
+    for (int start = 0; start < M; start += kIcpThreads) {
+        const int i = start + tid;
+        double x = 0, y = 0, z = 0;
+        bool in = false;
+        if (i < M) {
+            const size_t e = 3 * (size_t)(t0 + i);
+            x = ld_coord(tgt_xyz, pts_dtype, e);
+            y = ld_coord(tgt_xyz, pts_dtype, e + 1);
+            z = ld_coord(tgt_xyz, pts_dtype, e + 2);
+            in = inside_box(x, y, z, s_box);
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, in);
+        if (lane == 0) s_wcnt[warp] = __popc(bal);
+        __syncthreads();
+        int before = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < kIcpWarps; ++w) {
+            int c = s_wcnt[w];
+            before += (w < warp) ? c : 0;
+            total += c;
+        }
+        if (in) {
+            const long long pos = base + running + before + __popc(bal & ((1u << lane) - 1u));
+            qx[pos] = x;
+            qy[pos] = y;
+            qz[pos] = z;
+            qi[pos] = i;
+        }
+        running += total;
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// 3x3 SVD by two-sided Jacobi (Eigen JacobiSVD semantics): A = U diag(S) V^T,
+// S sorted descending and non-negative.  Static indices keep everything in registers.
+// ------------------------------------------------------------------------------------------
+template <int P, int Q>
+__device__ __forceinline__ void jacobi_pair(double (&W)[3][3], double (&U)[3][3], double (&V)[3][3],
+                                            double &maxdiag, bool &finished) {
+    const double tiny = 2.2250738585072014e-308;
+    const double thr = fmax(tiny, 4.440892098500626e-16 * maxdiag);
+    if (!(fabs(W[P][Q]) > thr || fabs(W[Q][P]) > thr)) return;
+    finished = false;
+    // 2x2 block on (Q,P), Q < P
+    const double m00 = W[Q][Q], m01 = W[Q][P], m10 = W[P][Q], m11 = W[P][P];
+    const double t = m00 + m11, d = m10 - m01;
+    double c1, s1;
+    if (fabs(d) < tiny) {
+        c1 = 1.0;
+        s1 = 0.0;
+    } else {
+        const double u = t / d, tmp = sqrt(1.0 + u * u);
+        s1 = 1.0 / tmp;
+        c1 = u / tmp;
+    }
+    const double a00 = c1 * m00 + s1 * m10, a01 = c1 * m01 + s1 * m11, a11 = -s1 * m01 + c1 * m11;
+    double c2, s2;
+    if (fabs(a01) < tiny) {
+        c2 = 1.0;
+        s2 = 0.0;
+    } else {
+        const double tau = (a00 - a11) / (2.0 * a01), w = sqrt(tau * tau + 1.0);
+        const double tn = (tau >= 0) ? -1.0 / (tau + w) : -1.0 / (tau - w);
+        c2 = 1.0 / sqrt(tn * tn + 1.0);
+        s2 = tn * c2;
+    }
+    const double cl = c2 * c1 + s2 * s1, sl = c2 * s1 - s2 * c1;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {  // rows (Q,P) <- L * rows
+        const double x = W[Q][j], y = W[P][j];
+        W[Q][j] = cl * x + sl * y;
+        W[P][j] = -sl * x + cl * y;
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {  // cols (Q,P) <- cols * J ; U <- U L^T ; V <- V J
+        double x = W[i][Q], y = W[i][P];
+        W[i][Q] = c2 * x - s2 * y;
+        W[i][P] = s2 * x + c2 * y;
+        x = U[i][Q];
+        y = U[i][P];
+        U[i][Q] = cl * x + sl * y;
+        U[i][P] = -sl * x + cl * y;
+        x = V[i][Q];
+        y = V[i][P];
+        V[i][Q] = c2 * x - s2 * y;
+        V[i][P] = s2 * x + c2 * y;
+    }
+    maxdiag = fmax(maxdiag, fmax(fabs(W[P][P]), fabs(W[Q][Q])));
+}
+
+template <int I, int K>
+__device__ __forceinline__ void swap_cols(double (&S)[3], double (&U)[3][3], double (&V)[3][3]) {
+    double t = S[I];
+    S[I] = S[K];
+    S[K] = t;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        t = U[r][I]; U[r][I] = U[r][K]; U[r][K] = t;
+        t = V[r][I]; V[r][I] = V[r][K]; V[r][K] = t;
+    }
+}
+
+__device__ __forceinline__ double det3(const double (&M)[3][3]) {
+    return M[0][0] * (M[1][1] * M[2][2] - M[1][2] * M[2][1]) - M[0][1] * (M[1][0] * M[2][2] - M[1][2] * M[2][0]) +
+           M[0][2] * (M[1][0] * M[2][1] - M[1][1] * M[2][0]);
+}
+
+// Kabsch rotation of a 3x3 covariance (Eigen umeyama without scaling): R = U diag(1,1,s) V^T
+__device__ void kabsch_rotation(const double (&sigma)[3][3], double (&R)[3][3]) {
+    double W[3][3], U[3][3], V[3][3];
+    double scale = 0.0;
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) scale = fmax(scale, fabs(sigma[i][j]));
+    if (scale == 0.0 || !(scale == scale)) scale = 1.0;
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            W[i][j] = sigma[i][j] / scale;
+            U[i][j] = V[i][j] = (i == j) ? 1.0 : 0.0;
+        }
+    double maxdiag = fmax(fabs(W[0][0]), fmax(fabs(W[1][1]), fabs(W[2][2])));
+    bool finished = false;
+    for (int sweep = 0; sweep < 64 && !finished; ++sweep) {
+        finished = true;
+        jacobi_pair<1, 0>(W, U, V, maxdiag, finished);
+        jacobi_pair<2, 0>(W, U, V, maxdiag, finished);
+        jacobi_pair<2, 1>(W, U, V, maxdiag, finished);
+    }
+    double S[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const double a = fabs(W[i][i]);
+        S[i] = a;
+        if (a != 0.0 && W[i][i] < 0.0) {
+#pragma unroll
+            for (int r = 0; r < 3; ++r) U[r][i] = -U[r][i];
+        }
+    }
+    // sort descending (3-element network equivalent to Eigen's selection sort on distinct values)
+    if (S[1] > S[0] && S[1] >= S[2]) swap_cols<0, 1>(S, U, V);
+    else if (S[2] > S[0] && S[2] > S[1]) swap_cols<0, 2>(S, U, V);
+    if (S[2] > S[1]) swap_cols<1, 2>(S, U, V);
+    const double sgn = (det3(U) * det3(V) < 0) ? -1.0 : 1.0;
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) R[r][c] = U[r][0] * V[c][0] + U[r][1] * V[c][1] + sgn * U[r][2] * V[c][2];
+}
+
+// ------------------------------------------------------------------------------------------
+// 4. fused per-tile ICP
+// ------------------------------------------------------------------------------------------
+struct IcpParams {
+    const void *src;
+    int pts_dtype;
+    const int *src_off;
+    const double *init_T;
+    double r2;
+    int max_iter;
+    double rel_fit, rel_rmse;
+    int ori_only;
+    const double *qx, *qy, *qz;
+    const int *qi;
+    const long long *toff;
+    const int *cnt;
+    const int *status_int;
+    double *pspill;
+    int p_cap;  // source points that fit in shared memory
+    double *out_T, *out_world;
+    int *out_corr;
+    double *out_fit, *out_rmse;
+    int *out_iters, *out_ntgt;
+};
+
+// x' = ((m0 x + m1 y) + m2 z) + m3, each operation rounded (open3d PointCloud::Transform)
+__device__ __forceinline__ double affine_row(const double *m, double x, double y, double z) {
+    return __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(m[0], x), __dmul_rn(m[1], y)), __dmul_rn(m[2], z)), m[3]);
+}
+
+__device__ __forceinline__ void transform_point(const double *T, bool affine, double &x, double &y, double &z) {
+    const double nx = affine_row(T, x, y, z), ny = affine_row(T + 4, x, y, z), nz = affine_row(T + 8, x, y, z);
+    if (affine) {  // last row (0,0,0,1): w == 1 exactly, the division is a bit-exact no-op
+        x = nx; y = ny; z = nz;
+    } else {
+        const double w = affine_row(T + 12, x, y, z);
+        x = nx / w; y = ny / w; z = nz / w;
+    }
+}
+
+__global__ void __launch_bounds__(kIcpThreads)
+icp_tiles_kernel(const IcpParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *sqx = reinterpret_cast<double *>(smem_raw);
+    double *sqy = sqx + kQChunk;
+    double *sqz = sqy + kQChunk;
+    double *spx_s = sqz + kQChunk;
+    double *spy_s = spx_s + p.p_cap;
+    double *spz_s = spy_s + p.p_cap;
+    int *scj_s = reinterpret_cast<int *>(spz_s + p.p_cap);
+
+    __shared__ double s_red[kIcpWarps][kNumSums];
+    __shared__ double s_U[16];
+    __shared__ double s_T[16];
+    __shared__ double s_prev[2];  // fitness, rmse of the previous correspondence pass
+    __shared__ int s_stop;
+    __shared__ __align__(8) uint64_t s_bar;
+
+    if (p.status_int[0]) return;  // compacted-target capacity exceeded: leave outputs untouched
+
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int s0 = p.src_off[b], ns = p.src_off[b + 1] - s0;
+    const int nt = p.cnt[b];
+    const long long q0 = p.toff[b];
+    const bool resident = nt <= kQChunk;
+    const int nchunks = (nt + kQChunk - 1) / kQChunk;
+
+    // source-point state: shared memory when it fits, else the global spill area
+    double *px, *py, *pz;
+    int *cj;
+    if (ns <= p.p_cap) {
+        px = spx_s; py = spy_s; pz = spz_s; cj = scj_s;
+    } else {
+        px = p.pspill + 3 * (size_t)s0; py = px + ns; pz = py + ns; cj = p.out_corr + s0;
+    }
+
+    if (tid == 0) {
+        mbar_init(&s_bar, 1);
+        mbar_fence_init();
+    }
+    if (tid < 16) s_T[tid] = p.init_T[16 * (size_t)b + tid];
+    __syncthreads();
+    uint32_t bar_phase = 0;
+
+    // stage one target chunk with the TMA engine: 3 bulk copies (x, y, z) on one mbarrier
+    auto load_chunk = [&](int c) {
+        const int n = min(kQChunk, nt - c * kQChunk);
+        const uint32_t bytes = (uint32_t)(((n + 1) & ~1) * sizeof(double));
+        if (tid == 0) {
+            fence_proxy_async();
+            mbar_arrive_expect_tx(&s_bar, 3 * bytes);
+            const long long o = q0 + (long long)c * kQChunk;
+            bulk_g2s(sqx, p.qx + o, bytes, &s_bar);
+            bulk_g2s(sqy, p.qy + o, bytes, &s_bar);
+            bulk_g2s(sqz, p.qz + o, bytes, &s_bar);
+        }
+        mbar_wait(&s_bar, bar_phase);
+        bar_phase ^= 1;
+    };
+    if (resident && nt > 0) load_chunk(0);
+
+    // P <- T0 * S
+    {
+        const bool aff0 = s_T[12] == 0.0 && s_T[13] == 0.0 && s_T[14] == 0.0 && s_T[15] == 1.0;
+        for (int i = tid; i < ns; i += kIcpThreads) {
+            const size_t e = 3 * (size_t)(s0 + i);
+            double x = ld_coord(p.src, p.pts_dtype, e), y = ld_coord(p.src, p.pts_dtype, e + 1),
+                   z = ld_coord(p.src, p.pts_dtype, e + 2);
+            transform_point(s_T, aff0, x, y, z);
+            px[i] = x; py[i] = y; pz[i] = z;
+        }
+    }
+    __syncthreads();
+
+    // split factor: S lanes share one source point when the tile is narrower than the CTA
+    int S = 1;
+    while (S < 32 && ns * (S * 2) <= kIcpThreads) S *= 2;
+    const int pts_per_round = kIcpThreads / S;
+    const int rounds = (ns + pts_per_round - 1) / pts_per_round;
+    const int sub = tid & (S - 1);
+    // moments are accumulated about the tile's first target point (kills cancellation)
+    const double ox = nt > 0 ? __ldg(p.qx + q0) : 0.0, oy = nt > 0 ? __ldg(p.qy + q0) : 0.0,
+                 oz = nt > 0 ? __ldg(p.qz + q0) : 0.0;
+
+    // one correspondence pass: fills cj[], leaves the 17 block-wide sums in s_red[0][*]
+    auto correspond = [&]() {
+        double acc[kNumSums];
+#pragma unroll
+        for (int k = 0; k < kNumSums; ++k) acc[k] = 0.0;
+        for (int r = 0; r < rounds; ++r) {
+            const int i = tid / S + r * pts_per_round;
+            const bool active = i < ns;
+            double x = 0, y = 0, z = 0;
+            if (active) { x = px[i]; y = py[i]; z = pz[i]; }
+            double bd = INFINITY;
+            int bj = -1;
+            for (int c = 0; c < nchunks; ++c) {
+                if (!resident) {
+                    __syncthreads();  // everyone done with the previous chunk
+                    load_chunk(c);
+                }
+                const int n = min(kQChunk, nt - c * kQChunk);
+                const int jbase = c * kQChunk;
+                if (active) {
+#pragma unroll 4
+                    for (int j = sub; j < n; j += S) {
+                        const double dx = __dsub_rn(x, sqx[j]), dy = __dsub_rn(y, sqy[j]), dz = __dsub_rn(z, sqz[j]);
+                        const double d = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+                        if (d < bd) { bd = d; bj = jbase + j; }
+                    }
+                }
+            }
+            // (d, j) lexicographic min across the S lanes of this point
+            for (int o = S >> 1; o > 0; o >>= 1) {
+                const double od = __shfl_xor_sync(0xffffffffu, bd, o);
+                const int oj = __shfl_xor_sync(0xffffffffu, bj, o);
+                if (oj >= 0 && (od < bd || (od == bd && oj < bj) || bj < 0)) { bd = od; bj = oj; }
+            }
+            if (active && sub == 0) {
+                const bool inl = bj >= 0 && bd < p.r2;
+                cj[i] = inl ? bj : -1;
+                if (inl) {
+                    double qx_, qy_, qz_;
+                    if (resident) { qx_ = sqx[bj]; qy_ = sqy[bj]; qz_ = sqz[bj]; }
+                    else { qx_ = __ldg(p.qx + q0 + bj); qy_ = __ldg(p.qy + q0 + bj); qz_ = __ldg(p.qz + q0 + bj); }
+                    const double ax = x - ox, ay = y - oy, az = z - oz;
+                    const double bx = qx_ - ox, by = qy_ - oy, bz = qz_ - oz;
+                    acc[0] += 1.0; acc[1] += bd;
+                    acc[2] += ax; acc[3] += ay; acc[4] += az;
+                    acc[5] += bx; acc[6] += by; acc[7] += bz;
+                    acc[8] += bx * ax; acc[9] += bx * ay; acc[10] += bx * az;
+                    acc[11] += by * ax; acc[12] += by * ay; acc[13] += by * az;
+                    acc[14] += bz * ax; acc[15] += bz * ay; acc[16] += bz * az;
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < kNumSums; ++k) acc[k] = warp_sum(acc[k]);
+        __syncthreads();  // s_red free (previous consumers done)
+        if (lane == 0) {
+#pragma unroll
+            for (int k = 0; k < kNumSums; ++k) s_red[warp][k] = acc[k];
+        }
+        __syncthreads();
+        if (tid < kNumSums) {
+            double t = s_red[0][tid];
+#pragma unroll
+            for (int w = 1; w < kIcpWarps; ++w) t += s_red[w][tid];
+            s_red[0][tid] = t;
+        }
+        __syncthreads();
+    };
+
+    correspond();
+    if (tid == 0) {
+        const double c = s_red[0][0];
+        s_prev[0] = c > 0 ? c / (double)ns : 0.0;
+        s_prev[1] = c > 0 ? sqrt(s_red[0][1] / c) : 0.0;
+    }
+
+    int iters = 0;
+    for (int it = 0; it < p.max_iter; ++it) {
+        if (tid == 0) {
+            // Kabsch / umeyama update from the block sums
+            const double c = s_red[0][0];
+            double Um[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+            if (c > 0) {
+                const double inv = 1.0 / c;
+                const double ma[3] = {s_red[0][2] * inv, s_red[0][3] * inv, s_red[0][4] * inv};
+                const double mb[3] = {s_red[0][5] * inv, s_red[0][6] * inv, s_red[0][7] * inv};
+                double sigma[3][3], R[3][3];
+#pragma unroll
+                for (int r = 0; r < 3; ++r)
+#pragma unroll
+                    for (int cc = 0; cc < 3; ++cc) sigma[r][cc] = s_red[0][8 + 3 * r + cc] * inv - mb[r] * ma[cc];
+                kabsch_rotation(sigma, R);
+                const double mua[3] = {ma[0] + ox, ma[1] + oy, ma[2] + oz};
+                const double mub[3] = {mb[0] + ox, mb[1] + oy, mb[2] + oz};
+#pragma unroll
+                for (int r = 0; r < 3; ++r) {
+                    Um[4 * r + 0] = R[r][0]; Um[4 * r + 1] = R[r][1]; Um[4 * r + 2] = R[r][2];
+                    Um[4 * r + 3] = mub[r] - (R[r][0] * mua[0] + R[r][1] * mua[1] + R[r][2] * mua[2]);
+                }
+            }
+            // T <- U * T (entries summed left to right, each operation rounded)
+            double Tn[16];
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int cc = 0; cc < 4; ++cc) {
+                    double s = __dmul_rn(Um[4 * r], s_T[cc]);
+                    s = __dadd_rn(s, __dmul_rn(Um[4 * r + 1], s_T[4 + cc]));
+                    s = __dadd_rn(s, __dmul_rn(Um[4 * r + 2], s_T[8 + cc]));
+                    s = __dadd_rn(s, __dmul_rn(Um[4 * r + 3], s_T[12 + cc]));
+                    Tn[4 * r + cc] = s;
+                }
+#pragma unroll
+            for (int k = 0; k < 16; ++k) { s_T[k] = Tn[k]; s_U[k] = Um[k]; }
+        }
+        __syncthreads();
+        // P <- U * P
+        for (int i = tid; i < ns; i += kIcpThreads) {
+            double x = px[i], y = py[i], z = pz[i];
+            transform_point(s_U, true, x, y, z);
+            px[i] = x; py[i] = y; pz[i] = z;
+        }
+        __syncthreads();
+        correspond();
+        if (tid == 0) {
+            const double c = s_red[0][0];
+            const double fit = c > 0 ? c / (double)ns : 0.0;
+            const double rmse = c > 0 ? sqrt(s_red[0][1] / c) : 0.0;
+            s_stop = (fabs(s_prev[0] - fit) < p.rel_fit && fabs(s_prev[1] - rmse) < p.rel_rmse) ? 1 : 0;
+            s_prev[0] = fit;
+            s_prev[1] = rmse;
+        }
+        __syncthreads();
+        iters = it + 1;
+        if (s_stop) break;
+    }
+
+    // outputs: pose (cluster_icp.py:161-165), world cluster = T * S (:167), correspondences
+    if (tid == 0) {
+        if (p.ori_only) {
+            s_T[3] = p.init_T[16 * (size_t)b + 3];
+            s_T[7] = p.init_T[16 * (size_t)b + 7];
+            s_T[11] = p.init_T[16 * (size_t)b + 11];
+        }
+        p.out_fit[b] = s_prev[0];
+        p.out_rmse[b] = s_prev[1];
+        p.out_iters[b] = iters;
+        p.out_ntgt[b] = nt;
+    }
+    __syncthreads();
+    if (tid < 16) p.out_T[16 * (size_t)b + tid] = s_T[tid];
+    const bool aff = s_T[12] == 0.0 && s_T[13] == 0.0 && s_T[14] == 0.0 && s_T[15] == 1.0;
+    for (int i = tid; i < ns; i += kIcpThreads) {
+        const size_t e = 3 * (size_t)(s0 + i);
+        double x = ld_coord(p.src, p.pts_dtype, e), y = ld_coord(p.src, p.pts_dtype, e + 1),
+               z = ld_coord(p.src, p.pts_dtype, e + 2);
+        transform_point(s_T, aff, x, y, z);
+        p.out_world[e] = x; p.out_world[e + 1] = y; p.out_world[e + 2] = z;
+        const int j = cj[i];
+        p.out_corr[s0 + i] = j >= 0 ? __ldg(p.qi + q0 + j) : -1;
+    }
+}
+
+}  // namespace aurdf
+
+// ------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------
+using namespace aurdf;
+
+extern "C" size_t aurdf_icp_workspace_bytes(int32_t n_tiles, int64_t total_src_points, int64_t tgt_capacity) {
+    if (n_tiles < 0 || total_src_points < 0 || tgt_capacity < 0) return 0;
+    return make_layout(n_tiles, total_src_points, tgt_capacity).total;
+}
+
+extern "C" int aurdf_icp_sweep_launches(void) { return 4; }
+
+extern "C" int aurdf_icp_sweep(const void *src_xyz, int pts_dtype, const int32_t *src_off, const void *tgt_xyz,
+                               const int32_t *tgt_off, const int32_t *tile_frame, const void *box_xyz,
+                               int box_dtype, const int32_t *box_off, const double *init_T, int32_t n_tiles,
+                               int64_t total_src_points, int32_t max_src_per_tile, double box_scale, double max_corr_dist, int32_t max_iter,
+                               double rel_fitness, double rel_rmse, int32_t ori_only, double *out_T,
+                               double *out_world_xyz, int32_t *out_corr, double *out_fitness, double *out_rmse,
+                               int32_t *out_iters, int32_t *out_ntgt, void *workspace, size_t workspace_bytes,
+                               int64_t tgt_capacity, int32_t *status, aurdf_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    AURDF_REQUIRE(n_tiles >= 0, "aurdf_icp_sweep: n_tiles < 0");
+    if (n_tiles == 0) return AURDF_OK;
+    AURDF_REQUIRE(max_corr_dist > 0.0, "aurdf_icp_sweep: max_corr_dist must be > 0 (open3d raises)");
+    AURDF_REQUIRE(max_iter >= 0, "aurdf_icp_sweep: max_iter < 0");
+    AURDF_REQUIRE(pts_dtype == AURDF_F32 || pts_dtype == AURDF_F64, "aurdf_icp_sweep: bad pts_dtype");
+    AURDF_REQUIRE(box_dtype == AURDF_F32 || box_dtype == AURDF_F64, "aurdf_icp_sweep: bad box_dtype");
+    AURDF_REQUIRE(src_off && tgt_off && tile_frame && init_T, "aurdf_icp_sweep: NULL input");
+    AURDF_REQUIRE(box_xyz == nullptr || box_off != nullptr, "aurdf_icp_sweep: box_xyz without box_off");
+    AURDF_REQUIRE(out_T && out_world_xyz && out_corr && out_fitness && out_rmse && out_iters && out_ntgt,
+                  "aurdf_icp_sweep: NULL output");
+    AURDF_REQUIRE(workspace && tgt_capacity >= 0, "aurdf_icp_sweep: NULL workspace");
+    AURDF_REQUIRE(((uintptr_t)workspace & 255) == 0, "aurdf_icp_sweep: workspace must be 256-byte aligned");
+
+    AURDF_REQUIRE(total_src_points >= 0, "aurdf_icp_sweep: total_src_points < 0");
+    const WsLayout L = make_layout(n_tiles, total_src_points, tgt_capacity);
+    if (workspace_bytes < L.total) {
+        set_error("aurdf_icp_sweep: workspace_bytes %zu < %zu", workspace_bytes, L.total);
+        return AURDF_EWORKSPACE;
+    }
+    char *ws = (char *)workspace;
+    double *box = (double *)(ws + L.box);
+    int *cnt = (int *)(ws + L.cnt);
+    long long *toff = (long long *)(ws + L.toff);
+    int *status_int = (int *)(ws + L.status);
+    double *qx = (double *)(ws + L.qx), *qy = (double *)(ws + L.qy), *qz = (double *)(ws + L.qz);
+    int *qi = (int *)(ws + L.qi);
+    double *pspill = (double *)(ws + L.pspill);
+
+    // source points live in shared memory up to p_cap per tile (bounded by the caller's hint and
+    // kPSmemMax); larger tiles keep them in the workspace spill area (sized by total_src_points)
+    int p_cap = max_src_per_tile > 0 ? max_src_per_tile : 256;
+    if (p_cap > kPSmemMax) p_cap = kPSmemMax;
+    p_cap = (p_cap + 1) & ~1;
+    const size_t smem = (size_t)3 * kQChunk * sizeof(double) + (size_t)3 * p_cap * sizeof(double) + (size_t)p_cap * sizeof(int);
+    if (smem > 48 * 1024)
+        AURDF_CUDA_CHECK(cudaFuncSetAttribute(icp_tiles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+
+    box_count_kernel<<<n_tiles, kIcpThreads, 0, stream>>>(box_xyz, box_dtype, box_off, tgt_xyz, pts_dtype, tgt_off,
+                                                          tile_frame, box_scale, box, cnt);
+    tile_scan_kernel<<<1, 1024, 0, stream>>>(cnt, n_tiles, (long long)tgt_capacity, toff, status_int, status);
+    mask_fill_kernel<<<n_tiles, kIcpThreads, 0, stream>>>(tgt_xyz, pts_dtype, tgt_off, tile_frame, box, toff,
+                                                          status_int, qx, qy, qz, qi);
+    IcpParams P;
+    P.src = src_xyz; P.pts_dtype = pts_dtype; P.src_off = src_off; P.init_T = init_T;
+    P.r2 = max_corr_dist * max_corr_dist; P.max_iter = max_iter; P.rel_fit = rel_fitness; P.rel_rmse = rel_rmse;
+    P.ori_only = ori_only;
+    P.qx = qx; P.qy = qy; P.qz = qz; P.qi = qi; P.toff = toff; P.cnt = cnt; P.status_int = status_int;
+    P.pspill = pspill; P.p_cap = p_cap;
+    P.out_T = out_T; P.out_world = out_world_xyz; P.out_corr = out_corr; P.out_fit = out_fitness;
+    P.out_rmse = out_rmse; P.out_iters = out_iters; P.out_ntgt = out_ntgt;
+    icp_tiles_kernel<<<n_tiles, kIcpThreads, smem, stream>>>(P);
+    AURDF_CUDA_CHECK(cudaGetLastError());
+    return AURDF_OK;
+}

@@ -1,0 +1,180 @@
+/*
+ * aurdf.h -- C ABI of the B200-native cluster-registration engine (libaurdf.so).
+ *
+ * Drop-in boundary for ONE hot path of jl6017/AutoURDF: the per-frame, per-cluster
+ * point-to-point ICP sweep and the SE(3) / dual-quaternion helpers around it.
+ * Reference files cited below are relative to the AutoURDF repository root.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / C++ types cross this boundary;
+ *   - unless a function name ends in _host, every pointer is a DEVICE pointer on the
+ *     current CUDA device and the call is asynchronous on `stream`;
+ *   - the library allocates nothing on the device-pointer entry points: the caller owns
+ *     every buffer, including `workspace`;
+ *   - return value 0 = success, negative = AURDF_E* below; nothing throws; the message of
+ *     the last failure on this thread is available from aurdf_last_error_string();
+ *   - points are packed xyz triples (AoS, as numpy (n,3) arrays are), CSR int32 offsets
+ *     delimit ragged groups; poses are row-major 4x4 doubles; quaternions are real-first.
+ */
+#ifndef AURDF_H
+#define AURDF_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AURDF_VERSION 100
+
+#if defined(__GNUC__)
+#define AURDF_API __attribute__((visibility("default")))
+#else
+#define AURDF_API
+#endif
+
+typedef void *aurdf_stream_t; /* a cudaStream_t */
+
+enum {
+    AURDF_OK = 0,
+    AURDF_EINVAL = -1,     /* bad argument (NULL pointer, negative size, max_corr_dist <= 0 ...) */
+    AURDF_EWORKSPACE = -2, /* workspace_bytes smaller than aurdf_icp_workspace_bytes() */
+    AURDF_ECUDA = -3,      /* a CUDA runtime call failed */
+    AURDF_ECAPACITY = -4,  /* compacted-target capacity exceeded (host path only; see status[]) */
+    AURDF_ENOMEM = -5
+};
+
+enum { AURDF_F32 = 0, AURDF_F64 = 1 };
+
+AURDF_API int aurdf_version(void);
+AURDF_API const char *aurdf_last_error_string(void);
+
+/* ---------------------------------------------------------------------------------------
+ * Cluster-ICP sweep: replaces masked_icp(), PointCloud/cluster_icp.py:118-191, including
+ * the open3d registration_icp() call at :157-159, batched over B (frame, cluster) tiles.
+ *
+ * Per tile b (frame f = tile_frame[b]):
+ *   box      = AABB of box_xyz[box_off[b]..box_off[b+1]) inflated by box_scale about its
+ *              centre (cluster_icp.py:133-140; float32 arithmetic when box_dtype is F32,
+ *              as numpy does for the float32 prediction handed over by mlp_reg.py:121);
+ *   target   = points of frame f strictly inside the box, original order (:142-148);
+ *   ICP      = open3d 0.18 RegistrationICP, point-to-point, float64: init init_T[b],
+ *              max_corr_dist, max_iter, |d fitness| < rel_fitness && |d rmse| < rel_rmse;
+ *   out_T[b] = fitted pose (translation reset to the init's when ori_only, :161-163);
+ *   out_world_xyz = out_T[b] applied to the tile's source points (:167);
+ *   out_corr[i]   = index, in frame f's cloud, of the final correspondence of source
+ *                   point i, or -1; out_fitness/out_rmse/out_iters/out_ntgt per tile.
+ *
+ * box_xyz == NULL disables the mask (every point of frame f is a target): that is the plain
+ * registration_icp() of link.py:113-117 and Sim/evaluation.py:358-362.
+ * pts_dtype is the storage type of src_xyz and tgt_xyz; all arithmetic is float64.
+ * tgt_capacity is the number of compacted target points the workspace can hold (the sum
+ * over tiles of the masked-target counts, each rounded up to even).  status (device
+ * int32[4], optional): [0] = 1 if the capacity was exceeded (outputs are then untouched),
+ * [1..2] = low/high 32 bits of the capacity that would have been needed.
+ * total_src_points = src_off[n_tiles] (the host knows it; the offsets live on the device).
+ * max_src_per_tile: upper bound on any tile's source count (0 = unknown), used only to
+ * size shared memory; tiles above the shared-memory bound use the workspace spill area.
+ * ------------------------------------------------------------------------------------- */
+AURDF_API size_t aurdf_icp_workspace_bytes(int32_t n_tiles, int64_t total_src_points, int64_t tgt_capacity);
+
+AURDF_API int aurdf_icp_sweep(const void *src_xyz, int pts_dtype, const int32_t *src_off,
+                    const void *tgt_xyz, const int32_t *tgt_off, const int32_t *tile_frame,
+                    const void *box_xyz, int box_dtype, const int32_t *box_off,
+                    const double *init_T, int32_t n_tiles, int64_t total_src_points,
+                    int32_t max_src_per_tile,
+                    double box_scale, double max_corr_dist, int32_t max_iter,
+                    double rel_fitness, double rel_rmse, int32_t ori_only,
+                    double *out_T, double *out_world_xyz, int32_t *out_corr,
+                    double *out_fitness, double *out_rmse, int32_t *out_iters, int32_t *out_ntgt,
+                    void *workspace, size_t workspace_bytes, int64_t tgt_capacity,
+                    int32_t *status, aurdf_stream_t stream);
+
+/* Number of kernels one aurdf_icp_sweep() call launches (for launch accounting). */
+AURDF_API int aurdf_icp_sweep_launches(void);
+
+/* ---------------------------------------------------------------------------------------
+ * Host-buffer path: same operator with HOST pointers.  A context owns a stream, pinned
+ * staging and growable device buffers; the call copies inputs host->device, runs the sweep,
+ * copies results device->host and returns when they are in place.  This is what a
+ * reference-side binding calls from the numpy world of mlp_reg.py:325.
+ * ------------------------------------------------------------------------------------- */
+typedef struct aurdf_ctx aurdf_ctx;
+
+AURDF_API int aurdf_ctx_create(int device, aurdf_ctx **out);
+AURDF_API void aurdf_ctx_destroy(aurdf_ctx *ctx);
+
+AURDF_API int aurdf_icp_sweep_host(aurdf_ctx *ctx,
+                         const void *src_xyz, int pts_dtype, const int32_t *src_off,
+                         const void *tgt_xyz, const int32_t *tgt_off, const int32_t *tile_frame,
+                         const void *box_xyz, int box_dtype, const int32_t *box_off,
+                         const double *init_T, int32_t n_tiles, int32_t n_frames,
+                         double box_scale, double max_corr_dist, int32_t max_iter,
+                         double rel_fitness, double rel_rmse, int32_t ori_only,
+                         double *out_T, double *out_world_xyz, int32_t *out_corr,
+                         double *out_fitness, double *out_rmse, int32_t *out_iters, int32_t *out_ntgt);
+
+/* bytes moved host->device / device->host by the last aurdf_icp_sweep_host() on ctx */
+AURDF_API void aurdf_ctx_last_copy_bytes(const aurdf_ctx *ctx, int64_t *h2d, int64_t *d2h);
+
+/* ---------------------------------------------------------------------------------------
+ * Nearest neighbour under squared L2 (float64 arithmetic, lowest index on exact ties):
+ * the correspondence search of open3d GetRegistrationResultAndCorrespondences, exposed on
+ * its own for B independent (query group, target group) pairs.
+ *   n_queries   = query_off[n_groups] (total query points; sizes the grid)
+ *   out_idx[i]  index within the group's target range, -1 if the group has no target
+ *   out_d2[i]   squared distance (may be NULL)
+ * ------------------------------------------------------------------------------------- */
+AURDF_API int aurdf_nn_l2(const void *query_xyz, const int32_t *query_off, const void *target_xyz,
+                const int32_t *target_off, int pts_dtype, int32_t n_groups, int64_t n_queries,
+                int32_t *out_idx, double *out_d2, aurdf_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * SE(3) apply: calculate_pc(), PointCloud/mlp_reg.py:155-170:  out = X @ R_k^T + t_k for
+ * every point of group k (dtype F32 or F64 for points, poses and output alike).
+ * aurdf_se3_apply_bwd is its adjoint for autograd: grad_X = g R_k, grad_T[k][:3,:3] =
+ * sum g^T x, grad_T[k][:3,3] = sum g, bottom row 0 (fully overwritten; grad_xyz or grad_T may
+ * be NULL to skip that half).
+ * aurdf_se3_to_local: inv(T_k) @ [X;1], mlp_reg.py:211-213 and cluster_icp.py:96-98
+ * (general 4x4 inverse, float64).
+ * ------------------------------------------------------------------------------------- */
+AURDF_API int aurdf_se3_apply(const void *xyz, const int32_t *off, const void *T, int32_t n_groups,
+                    int64_t n_points, int dtype, void *out_xyz, aurdf_stream_t stream);
+AURDF_API int aurdf_se3_apply_bwd(const void *grad_out, const void *xyz, const int32_t *off, const void *T,
+                        int32_t n_groups, int64_t n_points, int dtype, void *grad_xyz, void *grad_T,
+                        aurdf_stream_t stream);
+AURDF_API int aurdf_se3_to_local(const double *xyz, const int32_t *off, const double *T, int32_t n_groups,
+                       int64_t n_points, double *out_xyz, aurdf_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Dual-quaternion library: PointCloud/dq_func.py:4-257 and the four pytorch3d 0.7.7
+ * rotation_conversions functions it imports (dq_func.py:2).  n = number of batch elements,
+ * dtype F32 or F64, arithmetic in that dtype in the reference's operation order.
+ * ------------------------------------------------------------------------------------- */
+enum {
+    AURDF_DQ_TRANSFORM_FROM_ROT_TRANS = 0, /* (R 3x3, t 3)      -> T 4x4        dq_func.py:4   */
+    AURDF_DQ_QUATERNION_CONJUGATE = 1,     /* q 4               -> q 4          :29            */
+    AURDF_DQ_QUAT_TRANS_TO_DUALQUAT = 2,   /* (q 4, t 3)        -> dq 8         :47            */
+    AURDF_DQ_ROT_TRANS_TO_DUALQUAT = 3,    /* (R 3x3, t 3)      -> dq 8         :72            */
+    AURDF_DQ_TRANSFORM_TO_DUALQUAT = 4,    /* T 4x4             -> dq 8         :100           */
+    AURDF_DQ_DUALQUAT_TO_QUAT_TRANS = 5,   /* dq 8              -> (q 4, t 3)   :126           */
+    AURDF_DQ_DUALQUAT_TO_ROT_TRANS = 6,    /* dq 8              -> (R 3x3, t 3) :148           */
+    AURDF_DQ_DUALQUAT_TO_TRANSFORM = 7,    /* dq 8              -> T 4x4        :170           */
+    AURDF_DQ_DUALQUAT_MULTIPLY = 8,        /* (dq 8, dq 8)      -> dq 8         :188           */
+    AURDF_DQ_DUALQUAT_INVERT = 9,          /* dq 8              -> dq 8         :213           */
+    AURDF_DQ_POINT_TO_DUALQUAT = 10,       /* p 3               -> dq 8         :238           */
+    AURDF_Q_RAW_MULTIPLY = 11,             /* (q 4, q 4)        -> q 4   pytorch3d             */
+    AURDF_Q_INVERT = 12,                   /* q 4               -> q 4   pytorch3d             */
+    AURDF_Q_TO_MATRIX = 13,                /* q 4               -> R 3x3 pytorch3d             */
+    AURDF_MATRIX_TO_Q = 14                 /* R 3x3             -> q 4   pytorch3d             */
+};
+/* in0/in1: inputs (in1 NULL for unary ops); out0/out1: outputs (out1 NULL unless the op
+ * has two).  Contiguous, batch-major. */
+AURDF_API int aurdf_dq_op(int op, const void *in0, const void *in1, void *out0, void *out1, int64_t n,
+                int dtype, aurdf_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AURDF_H */

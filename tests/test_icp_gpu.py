@@ -1,0 +1,161 @@
+"""GPU parity: CUDA cluster-ICP sweep (through the C ABI) vs the CPU oracle and the golden
+vectors produced by the reference's own cluster_icp.py.  Gates (north_star / SURVEY 8d):
+correspondence indices bit-exact, iteration counts equal, poses within 1e-5."""
+import os
+
+import numpy as np
+import pytest
+
+from helpers import assert_parity, cuda_sweep, oracle_sweep
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def synth():
+    from autourdf_b200 import synth
+    return synth
+
+
+def test_wx200_c1_parity(oracle, synth):
+    b = synth.make_config("wx200")
+    assert_parity(cuda_sweep(b), oracle_sweep(oracle, b), what="wx200")
+
+
+def test_wx200_5_c2_parity(oracle, synth):
+    b = synth.make_config("wx200_5")
+    g, o = cuda_sweep(b), oracle_sweep(oracle, b, use_kdtree=True)
+    assert_parity(g, o, what="wx200_5")
+    assert (o["ntgt"] == 0).any(), "config is expected to contain an empty-mask tile"
+
+
+def test_franka_c3_parity(oracle, synth):
+    b = synth.make_config("franka")
+    assert_parity(cuda_sweep(b), oracle_sweep(oracle, b, use_kdtree=True), what="franka")
+
+
+def test_allegro_c4_parity(oracle, synth):
+    b = synth.make_config("allegro_hand", n_seq=2)
+    assert_parity(cuda_sweep(b), oracle_sweep(oracle, b, use_kdtree=True), what="allegro")
+
+
+def test_f32_storage_same_result(oracle, synth):
+    """inputs are float32-representable, so float32 storage must give identical results"""
+    import torch
+    b = synth.make_config("wx200")
+    src32 = b.src.astype(np.float32).astype(np.float64)
+    b.src = src32                       # make the local clusters float32-representable too
+    o = oracle_sweep(oracle, b)
+    assert_parity(cuda_sweep(b, pts_dtype=torch.float32), o, what="f32 storage")
+    assert_parity(cuda_sweep(b, pts_dtype=torch.float64), o, what="f64 storage")
+
+
+@pytest.mark.parametrize("ori", [False, True])
+def test_golden_masked_icp(golden_dir, ori):
+    """the drop-in masked_icp vs outputs of the reference's own masked_icp (make_golden.py)"""
+    from autourdf_b200.cluster_icp import masked_icp
+    z = np.load(os.path.join(golden_dir, "masked_icp.npz"))
+    K = int(z["K"])
+    F = z["tgt_off"].shape[0] - 1
+    for f in range(F):
+        tiles = range(f * K, (f + 1) * K)
+        cl = [z["src"][z["src_off"][t]:z["src_off"][t + 1]] for t in tiles]
+        cw = [z["box"][z["box_off"][t]:z["box_off"][t + 1]] for t in tiles]
+        cloud = z["tgt"][z["tgt_off"][f]:z["tgt_off"][f + 1]]
+        mats = z["init_T"][f * K:(f + 1) * K].astype(np.float32)
+        w, m = masked_icp(cl, cw, cloud, mats, False, ori=ori)
+        assert m.dtype == np.float64 and m.shape == (K, 4, 4)
+        assert np.abs(m - z[f"f{f}_ori{int(ori)}_T"]).max() <= 1e-5
+        assert np.abs(np.concatenate(w) - z[f"f{f}_ori{int(ori)}_world"]).max() <= 1e-5
+        assert [x.shape for x in w] == [c.shape for c in cl]
+
+
+def test_golden_masked_icp_f64_box_scale_th(golden_dir):
+    from autourdf_b200.cluster_icp import masked_icp
+    z = np.load(os.path.join(golden_dir, "masked_icp.npz"))
+    K = int(z["K"])
+    for f in range(z["tgt_off"].shape[0] - 1):
+        tiles = range(f * K, (f + 1) * K)
+        cl = [z["src"][z["src_off"][t]:z["src_off"][t + 1]] for t in tiles]
+        cw = [z["box"][z["box_off"][t]:z["box_off"][t + 1]].astype(np.float64) for t in tiles]
+        cloud = z["tgt"][z["tgt_off"][f]:z["tgt_off"][f + 1]]
+        mats = z["init_T"][f * K:(f + 1) * K].astype(np.float32)
+        w, m = masked_icp(cl, cw, cloud, mats, False, ori=False, scale=1.5, th=0.02)
+        assert np.abs(m - z[f"f{f}_f64box_T"]).max() <= 1e-5
+        assert np.abs(np.concatenate(w) - z[f"f{f}_f64box_world"]).max() <= 1e-5
+
+
+def test_edge_cases(oracle):
+    """empty source cluster, empty mask, single point, threshold rejection, zip truncation"""
+    from autourdf_b200.cluster_icp import masked_icp
+    rng = np.random.default_rng(3)
+    cloud = rng.uniform(-0.2, 0.2, size=(500, 3)).astype(np.float32).astype(np.float64)
+    I = np.eye(4, dtype=np.float32)
+    far = np.eye(4, dtype=np.float32); far[:3, 3] = 5.0
+    cl = [cloud[:40] * 0.5, np.zeros((0, 3)), cloud[40:41].copy(), cloud[50:120] * 0.9, cloud[:30].copy()]
+    mats = [I, I, I, I, far]
+    cw = [(c @ m[:3, :3].T + m[:3, 3]).astype(np.float32) if c.shape[0] else np.zeros((1, 3), np.float32)
+          for c, m in zip(cl, mats)]
+    for th in (1, 0.004):
+        dg, do = {}, {}
+        wg, mg = masked_icp(cl, cw, cloud, mats + [I, I], th=th, _details=dg)   # extra matrices: truncated
+        wo, mo = oracle.masked_icp(cl, cw, cloud, mats, th=th, _details=do)
+        assert len(wg) == 5 and mg.shape == (5, 4, 4)
+        assert np.array_equal(dg["corr"], do["corr"]) and np.array_equal(dg["iters"], do["iters"])
+        assert np.array_equal(dg["ntgt"], do["ntgt"])
+        assert np.abs(mg - mo).max() <= 1e-5
+        assert np.array_equal(mg[4], far.astype(np.float64))            # empty mask -> init unchanged
+        assert wg[1].shape == (0, 3)
+    with pytest.raises(ValueError):
+        masked_icp([cl[0]], [np.zeros((0, 3), np.float32)], cloud, [I])
+    with pytest.raises(RuntimeError):
+        masked_icp([cl[0]], [cw[0]], cloud, [I], th=0)
+
+
+def test_registration_icp_callsites(oracle):
+    """link.py:113 (th=1, init=I, 1e5 iters) and evaluation.py:358 (th=0.01, 2e4 iters)"""
+    from autourdf_b200.cluster_icp import registration_icp
+    from scipy.spatial.transform import Rotation
+    rng = np.random.default_rng(11)
+    tgt = rng.uniform(-0.1, 0.1, size=(3000, 3))
+    Rm = Rotation.from_rotvec([0.02, -0.03, 0.025]).as_matrix()
+    src = (tgt[:2500] - [0.002, 0.001, -0.0015]) @ Rm + rng.normal(0, 2e-4, size=(2500, 3))
+    for th, it in ((1, 100000), (0.01, 20000)):
+        g = registration_icp(src, tgt, th, np.eye(4), max_iteration=it)
+        o = oracle.icp_p2p(src, tgt, th, np.eye(4), max_iter=it, use_kdtree=True)
+        assert g.iterations == o["iters"]
+        i = np.nonzero(o["corr"] >= 0)[0]
+        assert np.array_equal(g.correspondence_set, np.stack([i, o["corr"][i]], 1))
+        assert np.abs(g.transformation - o["T"]).max() <= 1e-5
+        assert abs(g.fitness - o["fitness"]) <= 1e-12 and abs(g.inlier_rmse - o["rmse"]) <= 1e-9
+
+
+def test_large_tiles_streaming_and_spill(oracle, synth):
+    """tiles whose target exceeds one shared-memory chunk (streamed via TMA) and whose source
+    exceeds the shared-memory bound (workspace spill) -- a C5 sweep point, small frame count"""
+    b = synth.make_batch(n_points=16384, n_clusters=4, n_seq=1, n_frames=3, dof=5, cid=5)
+    assert np.diff(b.src_off).max() > 2048
+    assert_parity(cuda_sweep(b), oracle_sweep(oracle, b, use_kdtree=True), what="large tiles")
+
+
+def test_permutation_invariance(synth):
+    """relabelling the target points must only relabel the correspondences"""
+    b = synth.make_config("wx200", n_frames=3)
+    g0 = cuda_sweep(b)
+    rng = np.random.default_rng(0)
+    b2 = synth.make_config("wx200", n_frames=3)
+    perms = []
+    for f in range(b.n_frames):
+        s, e = b.tgt_off[f], b.tgt_off[f + 1]
+        p = rng.permutation(e - s)
+        b2.tgt[s:e] = b.tgt[s:e][p]
+        perms.append(p)
+    g1 = cuda_sweep(b2)
+    for t in range(b.n_tiles):
+        f = b.tile_frame[t]
+        c0 = g0["corr"][b.src_off[t]:b.src_off[t + 1]]
+        c1 = g1["corr"][b.src_off[t]:b.src_off[t + 1]]
+        ok = c0 >= 0
+        assert np.array_equal(c0 >= 0, c1 >= 0)
+        assert np.array_equal(perms[f][c1[ok]], c0[ok])
+    assert np.abs(g0["T"] - g1["T"]).max() <= 1e-9
