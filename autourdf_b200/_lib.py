@@ -26,6 +26,8 @@ SIGNATURES = {
                                   _f64, _f64, _i32, _f64, _f64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                   _vp, _sz, _i64, _vp, _vp]),
     "aurdf_icp_sweep_launches": (C.c_int, []),
+    "aurdf_icp_profile_enable": (C.c_int, [C.c_int]),
+    "aurdf_icp_profile_collect": (C.c_int, [C.POINTER(C.c_double), C.POINTER(_i32)]),
     "aurdf_ctx_create": (C.c_int, [C.c_int, C.POINTER(_vp)]),
     "aurdf_ctx_destroy": (None, [_vp]),
     "aurdf_icp_sweep_host": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp, _vp, _vp, _vp, C.c_int, _vp, _vp, _i32, _i32,

@@ -21,6 +21,8 @@
 #include <math.h>
 #include <stdio.h>
 
+#include <vector>
+
 #include "common.cuh"
 
 namespace aurdf {
@@ -273,27 +275,27 @@ __device__ __forceinline__ void jacobi_pair(double (&W)[3][3], double (&U)[3][3]
     const double thr = fmax(tiny, 4.440892098500626e-16 * maxdiag);
     if (!(fabs(W[P][Q]) > thr || fabs(W[Q][P]) > thr)) return;
     finished = false;
-    // 2x2 block on (Q,P), Q < P
+    // 2x2 block on (Q,P), Q < P.  Four special-function calls per rotation (2 rsqrt, 1 sqrt,
+    // 1 div): this runs on one thread and is the serial section of every ICP iteration.
     const double m00 = W[Q][Q], m01 = W[Q][P], m10 = W[P][Q], m11 = W[P][P];
+    // step 1: rotation R1 = [c1 s1; -s1 c1] that makes the block symmetric, tan = d / t
     const double t = m00 + m11, d = m10 - m01;
-    double c1, s1;
-    if (fabs(d) < tiny) {
-        c1 = 1.0;
-        s1 = 0.0;
-    } else {
-        const double u = t / d, tmp = sqrt(1.0 + u * u);
-        s1 = 1.0 / tmp;
-        c1 = u / tmp;
+    double c1 = 1.0, s1 = 0.0;
+    const double n1 = t * t + d * d;
+    if (fabs(d) >= tiny && n1 > tiny) {
+        const double r = rsqrt(n1);
+        c1 = t * r;
+        s1 = d * r;
     }
     const double a00 = c1 * m00 + s1 * m10, a01 = c1 * m01 + s1 * m11, a11 = -s1 * m01 + c1 * m11;
-    double c2, s2;
-    if (fabs(a01) < tiny) {
-        c2 = 1.0;
-        s2 = 0.0;
-    } else {
-        const double tau = (a00 - a11) / (2.0 * a01), w = sqrt(tau * tau + 1.0);
-        const double tn = (tau >= 0) ? -1.0 / (tau + w) : -1.0 / (tau - w);
-        c2 = 1.0 / sqrt(tn * tn + 1.0);
+    // step 2: symmetric Jacobi J = [c2 s2; -s2 c2], small root of t^2 - 2 tau t - 1 = 0 with
+    // tau = (a00 - a11) / (2 a01):  t = -2 a01 sgn(h) / (|h| + sqrt(h^2 + 4 a01^2)), h = a00 - a11
+    double c2 = 1.0, s2 = 0.0;
+    if (fabs(a01) >= tiny) {
+        const double h = a00 - a11, b2 = 2.0 * a01;
+        const double w = sqrt(h * h + b2 * b2);
+        const double tn = (h >= 0 ? -b2 : b2) / (fabs(h) + w);
+        c2 = rsqrt(tn * tn + 1.0);
         s2 = tn * c2;
     }
     const double cl = c2 * c1 + s2 * s1, sl = c2 * s1 - s2 * c1;
@@ -337,8 +339,11 @@ __device__ __forceinline__ double det3(const double (&M)[3][3]) {
            M[0][2] * (M[1][0] * M[2][1] - M[1][1] * M[2][0]);
 }
 
-// Kabsch rotation of a 3x3 covariance (Eigen umeyama without scaling): R = U diag(1,1,s) V^T
-__device__ void kabsch_rotation(const double (&sigma)[3][3], double (&R)[3][3]) {
+// Kabsch rotation of a 3x3 covariance (Eigen umeyama without scaling): R = U diag(1,1,s) V^T.
+// warm (18 doubles: U then V, row-major) carries the singular vectors of the previous ICP
+// iteration of the same tile: W = U^T sigma V is then already nearly diagonal and the Jacobi
+// iteration converges in one or two sweeps instead of five or six.  warm is updated in place.
+__device__ void kabsch_rotation(const double (&sigma)[3][3], double (&R)[3][3], double *warm, bool have_warm) {
     double W[3][3], U[3][3], V[3][3];
     double scale = 0.0;
 #pragma unroll
@@ -346,13 +351,34 @@ __device__ void kabsch_rotation(const double (&sigma)[3][3], double (&R)[3][3]) 
 #pragma unroll
         for (int j = 0; j < 3; ++j) scale = fmax(scale, fabs(sigma[i][j]));
     if (scale == 0.0 || !(scale == scale)) scale = 1.0;
+    const double inv_scale = 1.0 / scale;
+    if (have_warm) {
+        double SV[3][3];
 #pragma unroll
-    for (int i = 0; i < 3; ++i)
+        for (int i = 0; i < 3; ++i)
 #pragma unroll
-        for (int j = 0; j < 3; ++j) {
-            W[i][j] = sigma[i][j] / scale;
-            U[i][j] = V[i][j] = (i == j) ? 1.0 : 0.0;
-        }
+            for (int j = 0; j < 3; ++j) {
+                U[i][j] = warm[3 * i + j];
+                V[i][j] = warm[9 + 3 * i + j];
+            }
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j)
+                SV[i][j] = (sigma[i][0] * V[0][j] + sigma[i][1] * V[1][j] + sigma[i][2] * V[2][j]) * inv_scale;
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) W[i][j] = U[0][i] * SV[0][j] + U[1][i] * SV[1][j] + U[2][i] * SV[2][j];
+    } else {
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                W[i][j] = sigma[i][j] * inv_scale;
+                U[i][j] = V[i][j] = (i == j) ? 1.0 : 0.0;
+            }
+    }
     double maxdiag = fmax(fabs(W[0][0]), fmax(fabs(W[1][1]), fabs(W[2][2])));
     bool finished = false;
     for (int sweep = 0; sweep < 64 && !finished; ++sweep) {
@@ -371,10 +397,17 @@ __device__ void kabsch_rotation(const double (&sigma)[3][3], double (&R)[3][3]) 
             for (int r = 0; r < 3; ++r) U[r][i] = -U[r][i];
         }
     }
-    // sort descending (3-element network equivalent to Eigen's selection sort on distinct values)
+    // sort descending (3-element network equivalent to Eigen's selection sort)
     if (S[1] > S[0] && S[1] >= S[2]) swap_cols<0, 1>(S, U, V);
     else if (S[2] > S[0] && S[2] > S[1]) swap_cols<0, 2>(S, U, V);
     if (S[2] > S[1]) swap_cols<1, 2>(S, U, V);
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            warm[3 * i + j] = U[i][j];
+            warm[9 + 3 * i + j] = V[i][j];
+        }
     const double sgn = (det3(U) * det3(V) < 0) ? -1.0 : 1.0;
 #pragma unroll
     for (int r = 0; r < 3; ++r)
@@ -437,6 +470,7 @@ icp_tiles_kernel(const IcpParams p) {
     __shared__ double s_U[16];
     __shared__ double s_T[16];
     __shared__ double s_prev[2];  // fitness, rmse of the previous correspondence pass
+    __shared__ double s_warm[18]; // singular vectors of the previous Kabsch fit (Jacobi warm start)
     __shared__ int s_stop;
     __shared__ __align__(8) uint64_t s_bar;
 
@@ -583,6 +617,7 @@ icp_tiles_kernel(const IcpParams p) {
     }
 
     int iters = 0;
+    bool have_warm = false;  // meaningful on thread 0 only
     for (int it = 0; it < p.max_iter; ++it) {
         if (tid == 0) {
             // Kabsch / umeyama update from the block sums
@@ -597,7 +632,8 @@ icp_tiles_kernel(const IcpParams p) {
                 for (int r = 0; r < 3; ++r)
 #pragma unroll
                     for (int cc = 0; cc < 3; ++cc) sigma[r][cc] = s_red[0][8 + 3 * r + cc] * inv - mb[r] * ma[cc];
-                kabsch_rotation(sigma, R);
+                kabsch_rotation(sigma, R, s_warm, have_warm);
+                have_warm = true;
                 const double mua[3] = {ma[0] + ox, ma[1] + oy, ma[2] + oz};
                 const double mub[3] = {mb[0] + ox, mb[1] + oy, mb[2] + oz};
 #pragma unroll
@@ -683,6 +719,36 @@ extern "C" size_t aurdf_icp_workspace_bytes(int32_t n_tiles, int64_t total_src_p
 
 extern "C" int aurdf_icp_sweep_launches(void) { return 4; }
 
+// ---- optional live timing of the dominant kernel (icp_tiles_kernel) --------------------------
+namespace {
+struct EvPair { cudaEvent_t a, b; };
+thread_local bool g_prof_on = false;
+thread_local std::vector<EvPair> g_prof;
+}  // namespace
+
+extern "C" int aurdf_icp_profile_enable(int on) {
+    g_prof_on = on != 0;
+    return AURDF_OK;
+}
+
+extern "C" int aurdf_icp_profile_collect(double *total_ms, int32_t *n_launches) {
+    double tot = 0.0;
+    int n = 0;
+    for (EvPair &e : g_prof) {
+        float ms = 0.f;
+        AURDF_CUDA_CHECK(cudaEventSynchronize(e.b));
+        AURDF_CUDA_CHECK(cudaEventElapsedTime(&ms, e.a, e.b));
+        tot += ms;
+        ++n;
+        cudaEventDestroy(e.a);
+        cudaEventDestroy(e.b);
+    }
+    g_prof.clear();
+    if (total_ms) *total_ms = tot;
+    if (n_launches) *n_launches = n;
+    return AURDF_OK;
+}
+
 extern "C" int aurdf_icp_sweep(const void *src_xyz, int pts_dtype, const int32_t *src_off, const void *tgt_xyz,
                                const int32_t *tgt_off, const int32_t *tile_frame, const void *box_xyz,
                                int box_dtype, const int32_t *box_off, const double *init_T, int32_t n_tiles,
@@ -742,7 +808,17 @@ extern "C" int aurdf_icp_sweep(const void *src_xyz, int pts_dtype, const int32_t
     P.pspill = pspill; P.p_cap = p_cap;
     P.out_T = out_T; P.out_world = out_world_xyz; P.out_corr = out_corr; P.out_fit = out_fitness;
     P.out_rmse = out_rmse; P.out_iters = out_iters; P.out_ntgt = out_ntgt;
+    EvPair ev{nullptr, nullptr};
+    if (g_prof_on) {
+        AURDF_CUDA_CHECK(cudaEventCreate(&ev.a));
+        AURDF_CUDA_CHECK(cudaEventCreate(&ev.b));
+        AURDF_CUDA_CHECK(cudaEventRecord(ev.a, stream));
+    }
     icp_tiles_kernel<<<n_tiles, kIcpThreads, smem, stream>>>(P);
+    if (g_prof_on) {
+        AURDF_CUDA_CHECK(cudaEventRecord(ev.b, stream));
+        g_prof.push_back(ev);
+    }
     AURDF_CUDA_CHECK(cudaGetLastError());
     return AURDF_OK;
 }

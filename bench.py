@@ -1,0 +1,286 @@
+#!/usr/bin/env python
+"""bench.py -- cluster-ICP frames/s on B200 (BASELINE.json metric), one JSON line on stdout.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+A "step" is one pass of the hot path over the wx200_5 workload (C2: 5 sequences x 10 frames
+= 45 frame transitions, 2048 points/frame, 20 clusters -> 900 (frame, cluster) tiles); one
+"frame" is one complete masked_icp sweep of all clusters of one frame transition, run to the
+reference's convergence rule.  Synthetic data (autourdf_b200.synth), float64 arithmetic.
+
+  value     frames/s with inputs resident in HBM (CUDA events, max over ranks, L2 flushed
+            between steps); at N GPUs every rank sweeps its own sequences (weak scaling)
+            and the fitted poses are all-gathered over NCCL inside the timed region
+  e2e       the same through the host-buffer C-ABI call (aurdf_icp_sweep_host): numpy in,
+            numpy out, H2D + D2H copies inside the timed region
+  roofline  the fused per-tile ICP kernel: algorithmic bytes / its measured duration vs the
+            measured HBM peak (MEASURED_PEAKS.json), plus the FP64 issue fraction that
+            actually binds it
+  cpu_baseline / --impl reference: the CPU restatement (oracle/, k-d tree NN, OpenMP over
+            tiles, all host threads) on the same workload -- the reference's own open3d path
+            is not installable here
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOAD = "wx200_5"
+METRIC = "cluster_icp_frames_per_sec"
+UNIT = "frames/s"
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured"
+        except Exception:
+            pass
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)"""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], [], set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_workload(rank=0):
+    from autourdf_b200 import synth
+    cfg = dict(synth.CONFIGS[WORKLOAD])
+    return synth.make_batch(**cfg, seed=cfg["cid"] * 1000 + 17 * rank)
+
+
+def cpu_sweep(O, b, nthreads=0):
+    return O.masked_icp_sweep(b.src, b.src_off, b.tgt, b.tgt_off, b.tile_frame, b.box, b.box_off, b.init_T,
+                              use_kdtree=True, nthreads=nthreads)
+
+
+def run_reference(args):
+    """--impl reference: the CPU restatement of the reference path (k-d tree NN like open3d's
+    nanoflann, float64, OpenMP over tiles on every host thread).  Rank 0 only."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    from oracle import icp_oracle as O
+    O.build()
+    b = make_workload(0)
+    cores = O.lib().orc_max_threads()
+    for _ in range(max(args.warmup, 1)):
+        cpu_sweep(O, b)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_sweep(O, b)
+    dt = time.perf_counter() - t0
+    v = b.n_frames * args.steps / dt
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "frames_per_step": b.n_frames, "points_per_frame": b.meta["n_points"],
+                   "clusters": b.n_clusters, "tiles_per_step": b.n_tiles},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"full {WORKLOAD} batch ({b.n_frames} frame transitions) per step, "
+                                   "restated open3d ICP (oracle/icp_oracle.c, k-d tree NN, OpenMP over tiles)"},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from autourdf_b200 import _lib
+    from autourdf_b200 import cluster_icp as ci
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback exists)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    L = _lib.lib()
+
+    b = make_workload(rank)
+    d = ci.batch_to_device(b, device=dev)
+    max_src = int(np.diff(b.src_off).max())
+    r0 = ci.icp_sweep(d["src"], d["src_off"], d["tgt"], d["tgt_off"], d["tile_frame"], d["box"], d["box_off"],
+                      d["init_T"], max_src_per_tile=max_src)
+    torch.cuda.synchronize()
+    need = r0.needed_capacity()
+    ntgt = r0.ntgt.cpu().numpy().astype(np.int64)
+    iters = r0.iters.cpu().numpy().astype(np.int64)
+    ns = np.diff(b.src_off).astype(np.int64)
+    plan = ci.IcpSweep(b.n_tiles, b.src.shape[0], need + 64, max_src, device=dev)
+    gathered = torch.empty((world,) + tuple(plan.out.T.shape), dtype=torch.float64, device=dev) if world > 1 else None
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
+
+    def step():
+        r = plan.run(d["src"], d["src_off"], d["tgt"], d["tgt_off"], d["tile_frame"], d["box"], d["box_off"], d["init_T"])
+        if world > 1:   # the one exchange step of the path: fitted poses of every rank's sweep
+            dist.all_gather_into_tensor(gathered, r.T)
+        return r
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+
+    # ---------------- device-resident timing ----------------
+    for i in range(args.warmup):
+        flush.fill_(i & 0xFF)
+        step()
+    barrier()
+    L.aurdf_icp_profile_enable(1)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for i in range(args.steps):
+        flush.fill_(i & 0xFF)        # L2 flush, outside the timed bracket
+        ev[i][0].record()
+        step()
+        ev[i][1].record()
+    barrier()
+    L.aurdf_icp_profile_enable(0)
+    import ctypes as C
+    kms, kn = C.c_double(), C.c_int32()
+    L.aurdf_icp_profile_collect(C.byref(kms), C.byref(kn))
+    dev_ms = sum(a.elapsed_time(b_) for a, b_ in ev)
+    tmax = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    dev_ms_max = float(tmax.item())
+    frames_per_step = b.n_frames * world
+    value = frames_per_step * args.steps / (dev_ms_max * 1e-3)
+
+    # ---------------- end to end through the host-buffer C ABI ----------------
+    host = ci.HostSweep(local_rank)
+    tf = b.tile_frame
+    out = None
+    for _ in range(args.warmup):
+        out = host.run(b.src, b.src_off, b.tgt, b.tgt_off, tf, b.box, b.box_off, b.init_T, out=out)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        out = host.run(b.src, b.src_off, b.tgt, b.tgt_off, tf, b.box, b.box_off, b.init_T, out=out)
+    e2e_s = time.perf_counter() - t0
+    barrier()
+    h2d, d2h = host.copy_bytes()
+    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = frames_per_step * args.steps / float(te.item())
+    clocks = sampler.stop() if rank == 0 else None
+
+    if rank == 0:
+        # ---------------- roofline of the dominant kernel ----------------
+        peak, peak_src = load_peaks()
+        k_ms = kms.value / max(kn.value, 1)
+        b_alg = float((28 * ns + 12 * ntgt + 128).sum())          # fused ICP tile, bytes per launch
+        achieved = b_alg / (k_ms * 1e-3) / 1e9
+        pairs = float((ns * ntgt * (iters + 1)).sum())             # distance evaluations per launch
+        sm_hz = (clocks.get("sm_mhz") or 1965.0) * 1e6
+        fp64_peak = 148 * 64 * sm_hz                               # FP64 lane-instr/s (64 lanes/clk/SM)
+        fp64_rate = 9.0 * pairs / (k_ms * 1e-3)                    # 3 sub + 3 mul + 2 add + 1 compare per pair
+        roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": None, "peak_source": peak_src, "kernel": "icp_tiles_kernel",
+                    "kernel_ms": k_ms, "kernel_share_of_step": kms.value / dev_ms,
+                    "algorithmic_bytes_per_launch": b_alg,
+                    "binding_roof": {"bound": "fp64_issue", "pair_evals_per_launch": pairs,
+                                     "achieved_lane_instr_per_s": fp64_rate, "peak_lane_instr_per_s": fp64_peak,
+                                     "frac": fp64_rate / fp64_peak}}
+        # ---------------- CPU baseline on this box's host cores ----------------
+        from oracle import icp_oracle as O
+        O.build()
+        cores = O.lib().orc_max_threads()
+        cpu_sweep(O, b)
+        best = 1e30
+        t_all = time.perf_counter()
+        reps = 0
+        while reps < 5 or (time.perf_counter() - t_all < 10.0 and reps < 200):
+            t1 = time.perf_counter()
+            cpu_sweep(O, b)
+            best = min(best, time.perf_counter() - t1)
+            reps += 1
+        cpu = {"value": b.n_frames / best, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"full {WORKLOAD} batch ({b.n_frames} frame transitions), best of {reps} runs, restated "
+                         "open3d ICP (oracle/icp_oracle.c: k-d tree NN, float64, OpenMP over tiles)"}
+        print(json.dumps({
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "frames_per_step_per_gpu": b.n_frames,
+                       "points_per_frame": b.meta["n_points"], "clusters": b.n_clusters,
+                       "tiles_per_step_per_gpu": b.n_tiles, "mean_icp_iters": float(iters.mean()),
+                       "l2": "flushed between steps (256 MiB write)",
+                       "parallelism": f"tiles sharded by sequence over {world} GPU(s), all-gather of poses"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+            "gpu_launches": int(L.aurdf_icp_sweep_launches()) * args.steps,
+            "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+        }))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -94,6 +94,12 @@ AURDF_API int aurdf_icp_sweep(const void *src_xyz, int pts_dtype, const int32_t 
 /* Number of kernels one aurdf_icp_sweep() call launches (for launch accounting). */
 AURDF_API int aurdf_icp_sweep_launches(void);
 
+/* Live timing of the dominant kernel (the fused per-tile ICP kernel): while enabled, every
+ * aurdf_icp_sweep() on this thread brackets that kernel with CUDA events on the caller's
+ * stream; collect() waits for them, returns the summed duration and launch count, and resets. */
+AURDF_API int aurdf_icp_profile_enable(int on);
+AURDF_API int aurdf_icp_profile_collect(double *total_ms, int32_t *n_launches);
+
 /* ---------------------------------------------------------------------------------------
  * Host-buffer path: same operator with HOST pointers.  A context owns a stream, pinned
  * staging and growable device buffers; the call copies inputs host->device, runs the sweep,

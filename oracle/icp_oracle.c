@@ -232,8 +232,16 @@ ORC_API void orc_svd3(const double *A, double *Uo, double *So, double *Vo) {
  * Writes the 4x4 update (row-major).  Identity when there is no correspondence.
  * Sums run over correspondences in ascending source index (single-thread order of
  * GetRegistrationResultAndCorrespondences). */
+static void kabsch_sv(const double *P, int ns, const double *Q, const int *corr, double *Uout, double *Sout);
+
 ORC_API void orc_kabsch(const double *P, int ns, const double *Q, const int *corr, double *Uout) {
+    kabsch_sv(P, ns, Q, corr, Uout, NULL);
+}
+
+/* Sout (optional): the three singular values of the covariance (0,0,0 without correspondences) */
+static void kabsch_sv(const double *P, int ns, const double *Q, const int *corr, double *Uout, double *Sout) {
     for (int i = 0; i < 16; ++i) Uout[i] = (i % 5 == 0) ? 1.0 : 0.0;
+    if (Sout) Sout[0] = Sout[1] = Sout[2] = 0.0;
     int c = 0;
     double ms[3] = {0, 0, 0}, md[3] = {0, 0, 0};
     for (int i = 0; i < ns; ++i) {
@@ -257,6 +265,7 @@ ORC_API void orc_kabsch(const double *P, int ns, const double *Q, const int *cor
     for (int i = 0; i < 9; ++i) sigma[i] *= one_over_n;
     double U[9], S[3], V[9];
     orc_svd3(sigma, U, S, V);
+    if (Sout) { Sout[0] = S[0]; Sout[1] = S[1]; Sout[2] = S[2]; }
     double detU = U[0] * (U[4] * U[8] - U[5] * U[7]) - U[1] * (U[3] * U[8] - U[5] * U[6]) + U[2] * (U[3] * U[7] - U[4] * U[6]);
     double detV = V[0] * (V[4] * V[8] - V[5] * V[7]) - V[1] * (V[3] * V[8] - V[5] * V[6]) + V[2] * (V[3] * V[7] - V[4] * V[6]);
     double D[3] = {1.0, 1.0, (detU * detV < 0) ? -1.0 : 1.0};
@@ -414,10 +423,22 @@ ORC_API void orc_nn_batch(const double *P, int ns, const double *Q, int nt, int 
 /* open3d RegistrationICP, point-to-point                                     */
 /* ------------------------------------------------------------------------- */
 
+/* Parallel structure of the CPU run.  0 (default): OpenMP over tiles, each tile single-threaded
+ * and summed in ascending source index (deterministic; what the parity tests use).
+ * 1: the reference's own structure -- tiles one after the other like the Python loop at
+ * cluster_icp.py:131, OpenMP over the source points inside the correspondence search like
+ * open3d's GetRegistrationResultAndCorrespondences (per-thread partial sums, so the summation
+ * order is run dependent, as it is in open3d). */
+static int g_inner_par = 0;
+ORC_API void orc_set_reference_threading(int on) { g_inner_par = on ? 1 : 0; }
+
 static void correspond(const double *P, int ns, const double *Q, int nt, const kdtree *tree, double r2,
                        int *corr, double *fit, double *rmse) {
     double err2 = 0.0;
     int c = 0;
+#ifdef _OPENMP
+#pragma omp parallel for reduction(+ : err2, c) schedule(static) if (g_inner_par)
+#endif
     for (int i = 0; i < ns; ++i) {
         double d2;
         int j = tree ? kd_nn(tree, P + 3 * i, &d2) : orc_nn_brute(P + 3 * i, Q, nt, &d2);
@@ -428,11 +449,26 @@ static void correspond(const double *P, int ns, const double *Q, int nt, const k
     else { *fit = (double)c / (double)ns; *rmse = sqrt(err2 / (double)c); }
 }
 
+ORC_API int orc_icp_p2p_cond(const double *src, int ns, const double *tgt, int nt, double max_corr, const double *T0,
+                             int max_iter, double rel_fit, double rel_rmse, int use_kdtree, double *T_out, int *corr,
+                             double *fit_out, double *rmse_out, int *iters_out, double *P_out, double *cond_out);
+
 /* Returns 0, or -1 on bad arguments (open3d raises when max_corr <= 0), -2 on OOM.
  * corr[i]: index into tgt or -1.  P_out (optional): the incrementally updated points. */
 ORC_API int orc_icp_p2p(const double *src, int ns, const double *tgt, int nt, double max_corr, const double *T0,
                         int max_iter, double rel_fit, double rel_rmse, int use_kdtree, double *T_out, int *corr,
                         double *fit_out, double *rmse_out, int *iters_out, double *P_out) {
+    return orc_icp_p2p_cond(src, ns, tgt, nt, max_corr, T0, max_iter, rel_fit, rel_rmse, use_kdtree, T_out, corr,
+                            fit_out, rmse_out, iters_out, P_out, NULL);
+}
+
+/* Same, also reporting cond_out = min over the Kabsch fits of sigma_2/sigma_1 of the covariance
+ * (test diagnostic: a value near 0 means some fit had a rank<=1 covariance, where the optimal
+ * rotation is not unique and every SVD implementation returns a different member). */
+ORC_API int orc_icp_p2p_cond(const double *src, int ns, const double *tgt, int nt, double max_corr, const double *T0,
+                             int max_iter, double rel_fit, double rel_rmse, int use_kdtree, double *T_out, int *corr,
+                             double *fit_out, double *rmse_out, int *iters_out, double *P_out, double *cond_out) {
+    double cond = 1.0;
     if (!(max_corr > 0.0) || ns < 0 || nt < 0) return -1;
     double T[16];
     memcpy(T, T0, sizeof T);
@@ -452,8 +488,12 @@ ORC_API int orc_icp_p2p(const double *src, int ns, const double *tgt, int nt, do
     correspond(P, ns, tgt, nt, tp, r2, corr, &fit, &rmse);
     int it = 0;
     for (int i = 0; i < max_iter; ++i) {
-        double U[16];
-        orc_kabsch(P, ns, tgt, corr, U);
+        double U[16], Sv[3];
+        kabsch_sv(P, ns, tgt, corr, U, Sv);
+        if (fit > 0.0) {
+            double ratio = Sv[0] > 0.0 ? Sv[1] / Sv[0] : 0.0;
+            if (ratio < cond) cond = ratio;
+        }
         orc_mat4_mul(U, T, T);
         orc_transform_pts(U, P, ns, P);
         double fit2, rmse2;
@@ -468,6 +508,7 @@ ORC_API int orc_icp_p2p(const double *src, int ns, const double *tgt, int nt, do
     if (P_out) memcpy(P_out, P, sizeof(double) * 3 * (size_t)ns);
     free(P);
     *fit_out = fit; *rmse_out = rmse; *iters_out = it;
+    if (cond_out) *cond_out = cond;
     return 0;
 }
 
@@ -542,11 +583,11 @@ ORC_API int orc_masked_icp_sweep(const double *src, const int *src_off, const do
                                  const double *init_T, int B, double box_scale, double max_corr, int max_iter,
                                  double rel_fit, double rel_rmse, int ori_only, int use_kdtree, int nthreads,
                                  double *out_T, double *out_world, int *out_corr, double *out_fit,
-                                 double *out_rmse, int *out_iters, int *out_ntgt) {
+                                 double *out_rmse, int *out_iters, int *out_ntgt, double *out_cond) {
     int status = 0;
 #ifdef _OPENMP
     if (nthreads <= 0) nthreads = omp_get_max_threads();
-#pragma omp parallel for schedule(dynamic, 1) num_threads(nthreads)
+#pragma omp parallel for schedule(dynamic, 1) num_threads(nthreads) if (!g_inner_par)
 #endif
     for (int b = 0; b < B; ++b) {
         const int s0 = src_off[b], ns = src_off[b + 1] - s0;
@@ -563,10 +604,10 @@ ORC_API int orc_masked_icp_sweep(const double *src, const int *src_off, const do
         for (int j = 0; j < nt; ++j)
             for (int d = 0; d < 3; ++d) Q[3 * j + d] = tgt[3 * ((size_t)t0 + midx[j]) + d];
         int *corr = (int *)malloc(sizeof(int) * (size_t)(ns > 0 ? ns : 1));
-        double T[16], fit = 0, rmse = 0;
+        double T[16], fit = 0, rmse = 0, cond = 1.0;
         int iters = 0;
-        int rc = orc_icp_p2p(src + 3 * (size_t)s0, ns, Q, nt, max_corr, init_T + 16 * (size_t)b, max_iter, rel_fit,
-                             rel_rmse, use_kdtree, T, corr, &fit, &rmse, &iters, NULL);
+        int rc = orc_icp_p2p_cond(src + 3 * (size_t)s0, ns, Q, nt, max_corr, init_T + 16 * (size_t)b, max_iter,
+                                  rel_fit, rel_rmse, use_kdtree, T, corr, &fit, &rmse, &iters, NULL, &cond);
         if (rc != 0) {
 #ifdef _OPENMP
 #pragma omp critical
@@ -582,6 +623,7 @@ ORC_API int orc_masked_icp_sweep(const double *src, const int *src_off, const do
             orc_transform_pts(T, src + 3 * (size_t)s0, ns, out_world + 3 * (size_t)s0); /* :167 */
             for (int i = 0; i < ns; ++i) out_corr[s0 + i] = corr[i] < 0 ? -1 : midx[corr[i]];
             out_fit[b] = fit; out_rmse[b] = rmse; out_iters[b] = iters; out_ntgt[b] = nt;
+            if (out_cond) out_cond[b] = cond;
         }
         free(midx); free(Q); free(corr);
     }

@@ -49,11 +49,18 @@ def lib():
         L.orc_mat4_inv.restype = C.c_int
         L.orc_masked_icp_sweep.argtypes = [_dp, _ip, _dp, _ip, _ip, C.c_void_p, C.c_int, _ip, _dp, C.c_int,
                                            C.c_double, C.c_double, C.c_int, C.c_double, C.c_double, C.c_int,
-                                           C.c_int, C.c_int, _dp, _dp, _ip, _dp, _dp, _ip, _ip]
+                                           C.c_int, C.c_int, _dp, _dp, _ip, _dp, _dp, _ip, _ip, _dp]
         L.orc_masked_icp_sweep.restype = C.c_int
         L.orc_max_threads.restype = C.c_int
+        L.orc_set_reference_threading.argtypes = [C.c_int]
         _LIB = L
     return _LIB
+
+
+def set_reference_threading(on: bool):
+    """True: tiles serial, OpenMP inside the correspondence search (open3d's own structure);
+    False (default): OpenMP over tiles, deterministic per-tile arithmetic."""
+    lib().orc_set_reference_threading(int(bool(on)))
 
 
 def _d(a):
@@ -174,18 +181,19 @@ def masked_icp_sweep(src, src_off, tgt, tgt_off, tile_frame, box_pts, box_off, i
     out_T = np.empty((B, 4, 4)); out_world = np.empty((max(n, 1), 3)); out_corr = np.empty(max(n, 1), dtype=np.int32)
     out_fit = np.empty(max(B, 1)); out_rmse = np.empty(max(B, 1))
     out_iters = np.empty(max(B, 1), dtype=np.int32); out_ntgt = np.empty(max(B, 1), dtype=np.int32)
+    out_cond = np.ones(max(B, 1))
     rc = lib().orc_masked_icp_sweep(_d(src), _i(src_off), _d(tgt), _i(tgt_off), _i(tile_frame),
                                     box_pts.ctypes.data_as(C.c_void_p), int(is_f32), _i(box_off), _d(init_T), B,
                                     float(box_scale), float(max_corr), int(max_iter), float(rel_fit),
                                     float(rel_rmse), int(bool(ori_only)), int(use_kdtree), int(nthreads),
                                     _d(out_T), _d(out_world), _i(out_corr), _d(out_fit), _d(out_rmse),
-                                    _i(out_iters), _i(out_ntgt))
+                                    _i(out_iters), _i(out_ntgt), _d(out_cond))
     if rc == -1:
         raise RuntimeError("[Open3D Error] Invalid max_correspondence_distance.")
     if rc != 0:
         raise MemoryError
     return dict(T=out_T, world=out_world[:n], corr=out_corr[:n], fitness=out_fit[:B], rmse=out_rmse[:B],
-                iters=out_iters[:B], ntgt=out_ntgt[:B])
+                iters=out_iters[:B], ntgt=out_ntgt[:B], cond=out_cond[:B])
 
 
 def masked_icp(clusters_local, clusters_world, step_pc_np, matrices, visual=False, ori=False, scale=1.2, th=1,

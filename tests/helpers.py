@@ -18,15 +18,39 @@ def cuda_sweep(b, pts_dtype=None, **kw):
                 ntgt=r.ntgt.cpu().numpy())
 
 
-def assert_parity(g, o, pose_tol=1e-5, what=""):
+def ill_posed_tiles(b, o, rel=1e-6):
+    """Tiles in which some Kabsch fit of the ICP run had a rank<=1 covariance (the oracle reports
+    cond = min over iterations of sigma_2/sigma_1): fewer than 3 non-collinear matched points.
+    There the optimal rotation is a one-parameter family (free spin about the line); open3d/Eigen,
+    the oracle and the GPU each return one member and the runs diverge from that iteration on, so
+    these tiles are compared on mask counts and validity only.  They arise when an inflated box
+    holds 1-3 target points (thin clusters)."""
+    return np.nonzero(o["cond"] <= rel)[0]
+
+
+def assert_parity(g, o, pose_tol=1e-5, what="", batch=None):
     """bit-exact correspondence indices, masked counts and iteration counts; poses within 1e-5
-    (north_star tolerance); world points within 1e-5"""
+    (north_star tolerance); world points within 1e-5.  With ``batch`` given, rank-deficient
+    tiles (see ill_posed_tiles) are excluded from the pose comparison and must stay rare."""
     assert np.array_equal(g["ntgt"], o["ntgt"]), f"{what}: masked target counts differ"
-    bad = np.nonzero(g["corr"] != o["corr"])[0]
+    keep = np.ones(o["T"].shape[0], dtype=bool)
+    pkeep = np.ones(o["world"].shape[0], dtype=bool)
+    if batch is not None:
+        ill = ill_posed_tiles(batch, o)
+        assert ill.size <= max(1, 0.02 * batch.n_tiles), f"{what}: {ill.size} ill-posed tiles"
+        keep[ill] = False
+        for t in ill:
+            pkeep[batch.src_off[t]:batch.src_off[t + 1]] = False
+            R, Ro = g["T"][t][:3, :3], o["T"][t][:3, :3]      # still as rigid as the oracle's
+            assert np.abs(R @ R.T - np.eye(3)).max() <= np.abs(Ro @ Ro.T - np.eye(3)).max() + 1e-9
+            assert np.isfinite(g["T"][t]).all()
+    bad = np.nonzero((g["corr"] != o["corr"]) & pkeep)[0]
     assert bad.size == 0, f"{what}: {bad.size} correspondence indices differ, first at {bad[:5]}"
-    assert np.array_equal(g["iters"], o["iters"]), f"{what}: iteration counts differ at {np.nonzero(g['iters'] != o['iters'])[0][:5]}"
-    assert np.abs(g["T"] - o["T"]).max() <= pose_tol, f"{what}: pose error {np.abs(g['T'] - o['T']).max()}"
-    if g["world"].size:
-        assert np.abs(g["world"] - o["world"]).max() <= pose_tol
-    assert np.abs(g["fitness"] - o["fitness"]).max() <= 1e-12
-    assert np.abs(g["rmse"] - o["rmse"]).max() <= 1e-9
+    bad = np.nonzero((g["iters"] != o["iters"]) & keep)[0]
+    assert bad.size == 0, f"{what}: iteration counts differ at tiles {bad[:5]}"
+    assert np.abs(g["fitness"] - o["fitness"])[keep].max(initial=0) <= 1e-12
+    assert np.abs(g["rmse"] - o["rmse"])[keep].max(initial=0) <= 1e-9
+    err = np.abs(g["T"][keep] - o["T"][keep]).max() if keep.any() else 0.0
+    assert err <= pose_tol, f"{what}: pose error {err} at tile {np.abs(g['T'] - o['T']).reshape(len(keep), -1).max(1).argmax()}"
+    if pkeep.any():
+        assert np.abs(g["world"][pkeep] - o["world"][pkeep]).max() <= pose_tol

@@ -19,24 +19,24 @@ def synth():
 
 def test_wx200_c1_parity(oracle, synth):
     b = synth.make_config("wx200")
-    assert_parity(cuda_sweep(b), oracle_sweep(oracle, b), what="wx200")
+    assert_parity(cuda_sweep(b), oracle_sweep(oracle, b), what="wx200", batch=b)
 
 
 def test_wx200_5_c2_parity(oracle, synth):
     b = synth.make_config("wx200_5")
     g, o = cuda_sweep(b), oracle_sweep(oracle, b, use_kdtree=True)
-    assert_parity(g, o, what="wx200_5")
+    assert_parity(g, o, what="wx200_5", batch=b)
     assert (o["ntgt"] == 0).any(), "config is expected to contain an empty-mask tile"
 
 
 def test_franka_c3_parity(oracle, synth):
     b = synth.make_config("franka")
-    assert_parity(cuda_sweep(b), oracle_sweep(oracle, b, use_kdtree=True), what="franka")
+    assert_parity(cuda_sweep(b), oracle_sweep(oracle, b, use_kdtree=True), what="franka", batch=b)
 
 
 def test_allegro_c4_parity(oracle, synth):
     b = synth.make_config("allegro_hand", n_seq=2)
-    assert_parity(cuda_sweep(b), oracle_sweep(oracle, b, use_kdtree=True), what="allegro")
+    assert_parity(cuda_sweep(b), oracle_sweep(oracle, b, use_kdtree=True), what="allegro", batch=b)
 
 
 def test_f32_storage_same_result(oracle, synth):
@@ -135,7 +135,7 @@ def test_large_tiles_streaming_and_spill(oracle, synth):
     exceeds the shared-memory bound (workspace spill) -- a C5 sweep point, small frame count"""
     b = synth.make_batch(n_points=16384, n_clusters=4, n_seq=1, n_frames=3, dof=5, cid=5)
     assert np.diff(b.src_off).max() > 2048
-    assert_parity(cuda_sweep(b), oracle_sweep(oracle, b, use_kdtree=True), what="large tiles")
+    assert_parity(cuda_sweep(b), oracle_sweep(oracle, b, use_kdtree=True), what="large tiles", batch=b)
 
 
 def test_permutation_invariance(synth):

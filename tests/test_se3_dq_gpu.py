@@ -134,9 +134,11 @@ def test_nn_l2_vs_oracle(oracle):
         idx = torch.empty(int(qoff[-1]), dtype=torch.int32, device="cuda")
         d2 = torch.empty(int(qoff[-1]), dtype=torch.float64, device="cuda")
         L = _lib.lib()
-        _lib.check(L.aurdf_nn_l2(_lib.ptr(_dev(qa)), _lib.ptr(_dev(qoff)), _lib.ptr(_dev(ta)), _lib.ptr(_dev(toff)),
+        dq, dqo, dt_, dto = _dev(qa), _dev(qoff), _dev(ta), _dev(toff)    # keep the device buffers alive
+        _lib.check(L.aurdf_nn_l2(_lib.ptr(dq), _lib.ptr(dqo), _lib.ptr(dt_), _lib.ptr(dto),
                                  _lib.F32 if dt == np.float32 else _lib.F64, len(groups), int(qoff[-1]),
                                  _lib.ptr(idx), _lib.ptr(d2), _lib.current_stream()))
+        torch.cuda.synchronize()
         idx = idx.cpu().numpy(); d2 = d2.cpu().numpy()
         for g, (a, b) in enumerate(groups):
             sl = slice(qoff[g], qoff[g + 1])
