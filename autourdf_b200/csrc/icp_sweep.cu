@@ -31,7 +31,6 @@ constexpr int kIcpThreads = 128;
 constexpr int kIcpWarps = kIcpThreads / 32;
 constexpr int kQChunk = 512;      // target points staged per shared-memory chunk (12 KB as f64 SoA)
 constexpr int kPSmemMax = 2048;   // most source points a tile may keep in shared memory
-constexpr int kNumSums = 17;      // count, err2, sum p (3), sum q (3), sum q p^T (9)
 
 struct WsLayout {
     size_t box, cnt, toff, qx, qy, qz, qi, pspill, status, total;
@@ -267,7 +266,21 @@ mask_fill_kernel(const void *__restrict__ tgt_xyz, int pts_dtype, const int *__r
 // ------------------------------------------------------------------------------------------
 // 3x3 SVD by two-sided Jacobi (Eigen JacobiSVD semantics): A = U diag(S) V^T,
 // S sorted descending and non-negative.  Static indices keep everything in registers.
+// This is the serial section of every ICP iteration (one lane), so it is written for latency:
+// three reciprocal square roots per rotation and no division or square root.
 // ------------------------------------------------------------------------------------------
+
+// 1/sqrt(x) to ~1 ulp: MUFU.RSQ64H seed (rsqrt.approx.f64, ~20 bits) + two Newton steps.
+__device__ __forceinline__ double fast_rsqrt(double x) {
+    if (!(x > 1e-290 && x < 1e290)) return rsqrt(x);  // subnormal / huge / NaN: library path
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double hx = 0.5 * x;
+    y = y * (1.5 - hx * y * y);
+    y = y * (1.5 - hx * y * y);
+    return y;
+}
+
 template <int P, int Q>
 __device__ __forceinline__ void jacobi_pair(double (&W)[3][3], double (&U)[3][3], double (&V)[3][3],
                                             double &maxdiag, bool &finished) {
@@ -275,28 +288,32 @@ __device__ __forceinline__ void jacobi_pair(double (&W)[3][3], double (&U)[3][3]
     const double thr = fmax(tiny, 4.440892098500626e-16 * maxdiag);
     if (!(fabs(W[P][Q]) > thr || fabs(W[Q][P]) > thr)) return;
     finished = false;
-    // 2x2 block on (Q,P), Q < P.  Four special-function calls per rotation (2 rsqrt, 1 sqrt,
-    // 1 div): this runs on one thread and is the serial section of every ICP iteration.
+    // 2x2 block on (Q,P), Q < P
     const double m00 = W[Q][Q], m01 = W[Q][P], m10 = W[P][Q], m11 = W[P][P];
-    // step 1: rotation R1 = [c1 s1; -s1 c1] that makes the block symmetric, tan = d / t
+    // step 1: rotation R1 = [c1 s1; -s1 c1] that makes the block symmetric: (c1,s1) = (t,d)/|(t,d)|
     const double t = m00 + m11, d = m10 - m01;
     double c1 = 1.0, s1 = 0.0;
     const double n1 = t * t + d * d;
-    if (fabs(d) >= tiny && n1 > tiny) {
-        const double r = rsqrt(n1);
+    if (fabs(d) >= tiny && n1 > 1e-290) {
+        const double r = fast_rsqrt(n1);
         c1 = t * r;
         s1 = d * r;
     }
     const double a00 = c1 * m00 + s1 * m10, a01 = c1 * m01 + s1 * m11, a11 = -s1 * m01 + c1 * m11;
-    // step 2: symmetric Jacobi J = [c2 s2; -s2 c2], small root of t^2 - 2 tau t - 1 = 0 with
-    // tau = (a00 - a11) / (2 a01):  t = -2 a01 sgn(h) / (|h| + sqrt(h^2 + 4 a01^2)), h = a00 - a11
+    // step 2: symmetric Jacobi J = [c2 s2; -s2 c2] with tan = t2 the small root of
+    // t^2 - 2 tau t - 1 = 0, tau = h / (2 a01), h = a00 - a11:
+    //   (c2, s2) = (|h| + w, -sgn(h) 2 a01) / norm,  w = sqrt(h^2 + 4 a01^2)
     double c2 = 1.0, s2 = 0.0;
     if (fabs(a01) >= tiny) {
         const double h = a00 - a11, b2 = 2.0 * a01;
-        const double w = sqrt(h * h + b2 * b2);
-        const double tn = (h >= 0 ? -b2 : b2) / (fabs(h) + w);
-        c2 = rsqrt(tn * tn + 1.0);
-        s2 = tn * c2;
+        const double q = h * h + b2 * b2;
+        if (q > 1e-290) {
+            const double w = q * fast_rsqrt(q);
+            const double cx = fabs(h) + w, sx = (h >= 0 ? -b2 : b2);
+            const double r2 = fast_rsqrt(cx * cx + sx * sx);
+            c2 = cx * r2;
+            s2 = sx * r2;
+        }
     }
     const double cl = c2 * c1 + s2 * s1, sl = c2 * s1 - s2 * c1;
 #pragma unroll
@@ -342,16 +359,11 @@ __device__ __forceinline__ double det3(const double (&M)[3][3]) {
 // Kabsch rotation of a 3x3 covariance (Eigen umeyama without scaling): R = U diag(1,1,s) V^T.
 // warm (18 doubles: U then V, row-major) carries the singular vectors of the previous ICP
 // iteration of the same tile: W = U^T sigma V is then already nearly diagonal and the Jacobi
-// iteration converges in one or two sweeps instead of five or six.  warm is updated in place.
+// iteration converges in about two sweeps instead of six.  warm is updated in place.
+// (No pre-scaling by max|sigma|: the convergence threshold is relative and covariances of
+// metre-scale clouds are nowhere near the float64 range limits.)
 __device__ void kabsch_rotation(const double (&sigma)[3][3], double (&R)[3][3], double *warm, bool have_warm) {
     double W[3][3], U[3][3], V[3][3];
-    double scale = 0.0;
-#pragma unroll
-    for (int i = 0; i < 3; ++i)
-#pragma unroll
-        for (int j = 0; j < 3; ++j) scale = fmax(scale, fabs(sigma[i][j]));
-    if (scale == 0.0 || !(scale == scale)) scale = 1.0;
-    const double inv_scale = 1.0 / scale;
     if (have_warm) {
         double SV[3][3];
 #pragma unroll
@@ -364,8 +376,7 @@ __device__ void kabsch_rotation(const double (&sigma)[3][3], double (&R)[3][3], 
 #pragma unroll
         for (int i = 0; i < 3; ++i)
 #pragma unroll
-            for (int j = 0; j < 3; ++j)
-                SV[i][j] = (sigma[i][0] * V[0][j] + sigma[i][1] * V[1][j] + sigma[i][2] * V[2][j]) * inv_scale;
+            for (int j = 0; j < 3; ++j) SV[i][j] = sigma[i][0] * V[0][j] + sigma[i][1] * V[1][j] + sigma[i][2] * V[2][j];
 #pragma unroll
         for (int i = 0; i < 3; ++i)
 #pragma unroll
@@ -375,7 +386,7 @@ __device__ void kabsch_rotation(const double (&sigma)[3][3], double (&R)[3][3], 
         for (int i = 0; i < 3; ++i)
 #pragma unroll
             for (int j = 0; j < 3; ++j) {
-                W[i][j] = sigma[i][j] * inv_scale;
+                W[i][j] = sigma[i][j];
                 U[i][j] = V[i][j] = (i == j) ? 1.0 : 0.0;
             }
     }
@@ -413,6 +424,99 @@ __device__ void kabsch_rotation(const double (&sigma)[3][3], double (&R)[3][3], 
     for (int r = 0; r < 3; ++r)
 #pragma unroll
         for (int c = 0; c < 3; ++c) R[r][c] = U[r][0] * V[c][0] + U[r][1] * V[c][1] + sgn * U[r][2] * V[c][2];
+}
+
+// 1/x to ~2^-40: MUFU.RCP64H seed + one Newton step.  Only used inside Newton iterations that
+// self-correct, never for a value that is output.
+__device__ __forceinline__ double fast_rcp(double x) {
+    if (!(fabs(x) > 1e-290 && fabs(x) < 1e290)) return 1.0 / x;
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    y = y * (2.0 - x * y);
+    return y;
+}
+
+// Kabsch rotation for the common case, written for a short dependent chain (this is the
+// serial section of every ICP iteration).  The source points are re-posed every iteration, so
+// the optimal rotation R = argmax tr(R^T sigma) is near the identity.  R is optimal and proper
+// iff A = R^T sigma is symmetric positive definite (then R is the polar factor U V^T, which is
+// what umeyama returns when det(sigma) > 0).  Newton on SO(3): with S = sym(A) and
+// k = axial(A - A^T), solve (tr(S) I - S) w = k, rotate by the Cayley transform of w (an exact
+// rotation for any w), repeat; quadratic convergence, 2-4 steps.  Returns false when the result
+// cannot be certified (no convergence, A not positive definite: reflection or rank-deficient
+// input) and the caller falls back to the Jacobi SVD.
+__device__ bool kabsch_rotation_newton(const double (&sigma)[3][3], double (&R)[3][3]) {
+    double A[3][3];
+    double scale = 0.0;
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            A[i][j] = sigma[i][j];
+            R[i][j] = (i == j) ? 1.0 : 0.0;
+            scale = fmax(scale, fabs(sigma[i][j]));
+        }
+    if (!(scale > 1e-280 && scale < 1e280)) return false;
+    const double tol = 1e-16 * scale;  // below the rounding floor of A: only exact stationarity exits here
+    bool converged = false;
+    for (int step = 0; step < 8; ++step) {
+        const double kx = A[2][1] - A[1][2], ky = A[0][2] - A[2][0], kz = A[1][0] - A[0][1];
+        if (fmax(fabs(kx), fmax(fabs(ky), fabs(kz))) <= tol) {
+            converged = true;
+            break;
+        }
+        // G = tr(S) I - S (symmetric), S = sym(A)
+        const double s01 = 0.5 * (A[0][1] + A[1][0]), s02 = 0.5 * (A[0][2] + A[2][0]), s12 = 0.5 * (A[1][2] + A[2][1]);
+        const double g00 = A[1][1] + A[2][2], g11 = A[0][0] + A[2][2], g22 = A[0][0] + A[1][1];
+        const double g01 = -s01, g02 = -s02, g12 = -s12;
+        // w = G^-1 k by the adjugate
+        const double c00 = g11 * g22 - g12 * g12, c01 = g02 * g12 - g01 * g22, c02 = g01 * g12 - g02 * g11;
+        const double c11 = g00 * g22 - g02 * g02, c12 = g01 * g02 - g00 * g12, c22 = g00 * g11 - g01 * g01;
+        const double det = g00 * c00 + g01 * c01 + g02 * c02;
+        if (!(fabs(det) > 1e-280)) return false;
+        const double rdet = fast_rcp(det);
+        // v = w / 2
+        const double vx = 0.5 * rdet * (c00 * kx + c01 * ky + c02 * kz);
+        const double vy = 0.5 * rdet * (c01 * kx + c11 * ky + c12 * kz);
+        const double vz = 0.5 * rdet * (c02 * kx + c12 * ky + c22 * kz);
+        const double vv = vx * vx + vy * vy + vz * vz;
+        if (!(vv < 1.0)) return false;  // more than 90 degrees in one step: not the near-identity case
+        // Cayley: E = ((1 - vv) I + 2 v v^T + 2 [v]x) / (1 + vv), an exact rotation
+        const double rden = 1.0 / (1.0 + vv);
+        const double a = (1.0 - vv) * rden, b2 = 2.0 * rden;
+        double E[3][3];
+        E[0][0] = a + b2 * vx * vx; E[0][1] = b2 * (vx * vy - vz); E[0][2] = b2 * (vx * vz + vy);
+        E[1][0] = b2 * (vx * vy + vz); E[1][1] = a + b2 * vy * vy; E[1][2] = b2 * (vy * vz - vx);
+        E[2][0] = b2 * (vx * vz - vy); E[2][1] = b2 * (vy * vz + vx); E[2][2] = a + b2 * vz * vz;
+        double An[3][3], Rn[3][3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                An[i][j] = E[0][i] * A[0][j] + E[1][i] * A[1][j] + E[2][i] * A[2][j];  // E^T A
+                Rn[i][j] = R[i][0] * E[0][j] + R[i][1] * E[1][j] + R[i][2] * E[2][j];  // R E
+            }
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                A[i][j] = An[i][j];
+                R[i][j] = Rn[i][j];
+            }
+        // quadratic convergence: a step of |v| < 3e-9 leaves an error of ~|v|^2, below rounding
+        if (vv < 1e-17) {
+            converged = true;
+            break;
+        }
+    }
+    if (!converged) return false;
+    // certify the maximum: sym(A) positive definite with a margin (Sylvester), which also
+    // rejects det(sigma) <= 0 and near rank-deficient covariances
+    const double m1 = A[0][0];
+    const double m2 = A[0][0] * A[1][1] - A[0][1] * A[1][0];
+    const double m3 = det3(A);
+    const double eps = 1e-9;
+    return m1 > eps * scale && m2 > eps * scale * scale && m3 > eps * scale * scale * scale;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -455,7 +559,32 @@ __device__ __forceinline__ void transform_point(const double *T, bool affine, do
     }
 }
 
-__global__ void __launch_bounds__(kIcpThreads)
+// Sum 16 per-lane values over the 32 lanes of a warp with 16 shuffles (a transposing
+// butterfly: every step halves the number of values a lane carries).  Afterwards v[0] holds
+// the warp total of value number (lane >> 1).
+__device__ __forceinline__ void warp_sum16(double (&v)[16], int lane) {
+#pragma unroll
+    for (int half = 8, off = 16; half >= 1; half >>= 1, off >>= 1) {
+        const bool hi = (lane & off) != 0;
+#pragma unroll
+        for (int k = 0; k < half; ++k) {
+            const double send = hi ? v[k] : v[k + half];
+            const double keep = hi ? v[k + half] : v[k];
+            v[k] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+    }
+    v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+}
+
+// One CTA per tile, resident until that tile's ICP has converged.  Per iteration:
+//   pass      every warp: P <- U P (fused), brute-force NN of its source points against the
+//             target chunk in shared memory, 16 moment sums + inlier count per warp
+//   barrier A
+//   warp 0    lane 0: Kabsch / Jacobi-SVD pose update from the block totals -> U
+//   warp 1    lane 0: fitness, rmse and open3d's convergence test          -> stop flag
+//   barrier B
+//   warp 3    16 lanes: T <- U T (off the critical path, overlaps the next pass)
+__global__ void __launch_bounds__(kIcpThreads, 5)
 icp_tiles_kernel(const IcpParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *sqx = reinterpret_cast<double *>(smem_raw);
@@ -466,11 +595,13 @@ icp_tiles_kernel(const IcpParams p) {
     double *spz_s = spy_s + p.p_cap;
     int *scj_s = reinterpret_cast<int *>(spz_s + p.p_cap);
 
-    __shared__ double s_red[kIcpWarps][kNumSums];
-    __shared__ double s_U[16];
-    __shared__ double s_T[16];
-    __shared__ double s_prev[2];  // fitness, rmse of the previous correspondence pass
-    __shared__ double s_warm[18]; // singular vectors of the previous Kabsch fit (Jacobi warm start)
+    __shared__ double s_part[kIcpWarps][16];  // per-warp moment sums
+    __shared__ int s_cnt[kIcpWarps];          // per-warp inlier counts
+    __shared__ double s_tot[2][16];           // block totals, one copy per consumer warp
+    __shared__ double s_U[16];                // current update (row-major 4x4)
+    __shared__ double s_T[16];                // accumulated pose
+    __shared__ double s_prev[2];              // fitness, rmse of the previous pass
+    __shared__ double s_warm[18];             // singular vectors of the previous fit
     __shared__ int s_stop;
     __shared__ __align__(8) uint64_t s_bar;
 
@@ -495,8 +626,12 @@ icp_tiles_kernel(const IcpParams p) {
     if (tid == 0) {
         mbar_init(&s_bar, 1);
         mbar_fence_init();
+        s_stop = 0;
     }
-    if (tid < 16) s_T[tid] = p.init_T[16 * (size_t)b + tid];
+    if (tid < 16) {
+        s_T[tid] = p.init_T[16 * (size_t)b + tid];
+        s_U[tid] = (tid % 5 == 0) ? 1.0 : 0.0;
+    }
     __syncthreads();
     uint32_t bar_phase = 0;
 
@@ -540,16 +675,25 @@ icp_tiles_kernel(const IcpParams p) {
     const double ox = nt > 0 ? __ldg(p.qx + q0) : 0.0, oy = nt > 0 ? __ldg(p.qy + q0) : 0.0,
                  oz = nt > 0 ? __ldg(p.qz + q0) : 0.0;
 
-    // one correspondence pass: fills cj[], leaves the 17 block-wide sums in s_red[0][*]
-    auto correspond = [&]() {
-        double acc[kNumSums];
+    // One correspondence pass.  apply: first move the points by the current update s_U.
+    // Leaves per-warp partial sums in s_part / s_cnt (valid after the next barrier).
+    auto pass = [&](bool apply) {
+        double acc[16];
 #pragma unroll
-        for (int k = 0; k < kNumSums; ++k) acc[k] = 0.0;
+        for (int k = 0; k < 16; ++k) acc[k] = 0.0;
+        int cnt = 0;
         for (int r = 0; r < rounds; ++r) {
             const int i = tid / S + r * pts_per_round;
             const bool active = i < ns;
             double x = 0, y = 0, z = 0;
-            if (active) { x = px[i]; y = py[i]; z = pz[i]; }
+            if (active) {
+                x = px[i]; y = py[i]; z = pz[i];
+                if (apply) transform_point(s_U, true, x, y, z);
+            }
+            if (apply) {
+                if (S > 1) __syncwarp();  // the S lanes of a point have all read the old value
+                if (active && sub == 0) { px[i] = x; py[i] = y; pz[i] = z; }
+            }
             double bd = INFINITY;
             int bj = -1;
             for (int c = 0; c < nchunks; ++c) {
@@ -574,110 +718,125 @@ icp_tiles_kernel(const IcpParams p) {
                 const int oj = __shfl_xor_sync(0xffffffffu, bj, o);
                 if (oj >= 0 && (od < bd || (od == bd && oj < bj) || bj < 0)) { bd = od; bj = oj; }
             }
-            if (active && sub == 0) {
-                const bool inl = bj >= 0 && bd < p.r2;
-                cj[i] = inl ? bj : -1;
-                if (inl) {
-                    double qx_, qy_, qz_;
-                    if (resident) { qx_ = sqx[bj]; qy_ = sqy[bj]; qz_ = sqz[bj]; }
-                    else { qx_ = __ldg(p.qx + q0 + bj); qy_ = __ldg(p.qy + q0 + bj); qz_ = __ldg(p.qz + q0 + bj); }
-                    const double ax = x - ox, ay = y - oy, az = z - oz;
-                    const double bx = qx_ - ox, by = qy_ - oy, bz = qz_ - oz;
-                    acc[0] += 1.0; acc[1] += bd;
-                    acc[2] += ax; acc[3] += ay; acc[4] += az;
-                    acc[5] += bx; acc[6] += by; acc[7] += bz;
-                    acc[8] += bx * ax; acc[9] += bx * ay; acc[10] += bx * az;
-                    acc[11] += by * ax; acc[12] += by * ay; acc[13] += by * az;
-                    acc[14] += bz * ax; acc[15] += bz * ay; acc[16] += bz * az;
-                }
+            const bool inl = active && sub == 0 && bj >= 0 && bd < p.r2;
+            if (active && sub == 0) cj[i] = inl ? bj : -1;
+            cnt += __popc(__ballot_sync(0xffffffffu, inl));
+            if (inl) {
+                double qx_, qy_, qz_;
+                if (resident) { qx_ = sqx[bj]; qy_ = sqy[bj]; qz_ = sqz[bj]; }
+                else { qx_ = __ldg(p.qx + q0 + bj); qy_ = __ldg(p.qy + q0 + bj); qz_ = __ldg(p.qz + q0 + bj); }
+                const double ax = x - ox, ay = y - oy, az = z - oz;
+                const double bx = qx_ - ox, by = qy_ - oy, bz = qz_ - oz;
+                acc[0] += bd;
+                acc[1] += ax; acc[2] += ay; acc[3] += az;
+                acc[4] += bx; acc[5] += by; acc[6] += bz;
+                acc[7] += bx * ax; acc[8] += bx * ay; acc[9] += bx * az;
+                acc[10] += by * ax; acc[11] += by * ay; acc[12] += by * az;
+                acc[13] += bz * ax; acc[14] += bz * ay; acc[15] += bz * az;
             }
         }
-#pragma unroll
-        for (int k = 0; k < kNumSums; ++k) acc[k] = warp_sum(acc[k]);
-        __syncthreads();  // s_red free (previous consumers done)
-        if (lane == 0) {
-#pragma unroll
-            for (int k = 0; k < kNumSums; ++k) s_red[warp][k] = acc[k];
-        }
-        __syncthreads();
-        if (tid < kNumSums) {
-            double t = s_red[0][tid];
-#pragma unroll
-            for (int w = 1; w < kIcpWarps; ++w) t += s_red[w][tid];
-            s_red[0][tid] = t;
-        }
-        __syncthreads();
+        warp_sum16(acc, lane);
+        if ((lane & 1) == 0) s_part[warp][lane >> 1] = acc[0];
+        if (lane == 0) s_cnt[warp] = cnt;
     };
 
-    correspond();
-    if (tid == 0) {
-        const double c = s_red[0][0];
-        s_prev[0] = c > 0 ? c / (double)ns : 0.0;
-        s_prev[1] = c > 0 ? sqrt(s_red[0][1] / c) : 0.0;
+    // block totals for consumer warp w (0: pose fit, 1: convergence test); returns the count
+    auto totals = [&](int w) -> int {
+        if (lane < 16) {
+            double t = s_part[0][lane];
+#pragma unroll
+            for (int k = 1; k < kIcpWarps; ++k) t += s_part[k][lane];
+            s_tot[w][lane] = t;
+        }
+        int c = 0;
+#pragma unroll
+        for (int k = 0; k < kIcpWarps; ++k) c += s_cnt[k];
+        __syncwarp();
+        return c;
+    };
+
+    // Kabsch / umeyama update from the totals of consumer slot 0 (lane 0 of warp 0)
+    bool have_warm = false;
+    auto fit_pose = [&](int c) {
+        const double *t = s_tot[0];
+        double Um[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
+        if (c > 0) {
+            const double inv = 1.0 / (double)c;
+            const double ma[3] = {t[1] * inv, t[2] * inv, t[3] * inv};
+            const double mb[3] = {t[4] * inv, t[5] * inv, t[6] * inv};
+            double sigma[3][3], R[3][3];
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+#pragma unroll
+                for (int cc = 0; cc < 3; ++cc) sigma[r][cc] = t[7 + 3 * r + cc] * inv - mb[r] * ma[cc];
+            if (!kabsch_rotation_newton(sigma, R)) {
+                kabsch_rotation(sigma, R, s_warm, have_warm);  // reflection / rank-deficient / large step
+                have_warm = true;
+            }
+            const double mua[3] = {ma[0] + ox, ma[1] + oy, ma[2] + oz};
+            const double mub[3] = {mb[0] + ox, mb[1] + oy, mb[2] + oz};
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                Um[4 * r + 0] = R[r][0]; Um[4 * r + 1] = R[r][1]; Um[4 * r + 2] = R[r][2];
+                Um[4 * r + 3] = mub[r] - (R[r][0] * mua[0] + R[r][1] * mua[1] + R[r][2] * mua[2]);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 12; ++k) s_U[k] = Um[k];
+    };
+
+    // T <- U * T, one lane per entry, entries summed left to right with each operation rounded
+    auto compose_pose = [&]() {
+        double v = 0.0;
+        if (lane < 16) {
+            const int r = lane >> 2, cc = lane & 3;
+            v = __dmul_rn(s_U[4 * r], s_T[cc]);
+            v = __dadd_rn(v, __dmul_rn(s_U[4 * r + 1], s_T[4 + cc]));
+            v = __dadd_rn(v, __dmul_rn(s_U[4 * r + 2], s_T[8 + cc]));
+            v = __dadd_rn(v, __dmul_rn(s_U[4 * r + 3], s_T[12 + cc]));
+        }
+        __syncwarp();
+        if (lane < 16) s_T[lane] = v;
+    };
+
+    pass(false);
+    __syncthreads();  // barrier A
+    if (warp == 0) {
+        const int c = totals(0);
+        if (lane == 0 && p.max_iter > 0) fit_pose(c);
+    } else if (warp == 1) {
+        const int c = totals(1);
+        if (lane == 0) {
+            s_prev[0] = c > 0 ? (double)c / (double)ns : 0.0;
+            s_prev[1] = c > 0 ? sqrt(s_tot[1][0] / (double)c) : 0.0;
+        }
     }
+    __syncthreads();  // barrier B
 
     int iters = 0;
-    bool have_warm = false;  // meaningful on thread 0 only
     for (int it = 0; it < p.max_iter; ++it) {
-        if (tid == 0) {
-            // Kabsch / umeyama update from the block sums
-            const double c = s_red[0][0];
-            double Um[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
-            if (c > 0) {
-                const double inv = 1.0 / c;
-                const double ma[3] = {s_red[0][2] * inv, s_red[0][3] * inv, s_red[0][4] * inv};
-                const double mb[3] = {s_red[0][5] * inv, s_red[0][6] * inv, s_red[0][7] * inv};
-                double sigma[3][3], R[3][3];
-#pragma unroll
-                for (int r = 0; r < 3; ++r)
-#pragma unroll
-                    for (int cc = 0; cc < 3; ++cc) sigma[r][cc] = s_red[0][8 + 3 * r + cc] * inv - mb[r] * ma[cc];
-                kabsch_rotation(sigma, R, s_warm, have_warm);
-                have_warm = true;
-                const double mua[3] = {ma[0] + ox, ma[1] + oy, ma[2] + oz};
-                const double mub[3] = {mb[0] + ox, mb[1] + oy, mb[2] + oz};
-#pragma unroll
-                for (int r = 0; r < 3; ++r) {
-                    Um[4 * r + 0] = R[r][0]; Um[4 * r + 1] = R[r][1]; Um[4 * r + 2] = R[r][2];
-                    Um[4 * r + 3] = mub[r] - (R[r][0] * mua[0] + R[r][1] * mua[1] + R[r][2] * mua[2]);
-                }
+        if (warp == kIcpWarps - 1) compose_pose();  // uses s_U of this iteration; next write is after barrier A
+        pass(true);
+        __syncthreads();  // barrier A
+        if (warp == 0) {
+            // speculative: the fit for iteration it+1 runs while warp 1 decides whether to stop
+            const int c = totals(0);
+            if (lane == 0 && it + 1 < p.max_iter) fit_pose(c);
+        } else if (warp == 1) {
+            const int c = totals(1);
+            if (lane == 0) {
+                const double fit = c > 0 ? (double)c / (double)ns : 0.0;
+                const double rmse = c > 0 ? sqrt(s_tot[1][0] / (double)c) : 0.0;
+                s_stop = (fabs(s_prev[0] - fit) < p.rel_fit && fabs(s_prev[1] - rmse) < p.rel_rmse) ? 1 : 0;
+                s_prev[0] = fit;
+                s_prev[1] = rmse;
             }
-            // T <- U * T (entries summed left to right, each operation rounded)
-            double Tn[16];
-#pragma unroll
-            for (int r = 0; r < 4; ++r)
-#pragma unroll
-                for (int cc = 0; cc < 4; ++cc) {
-                    double s = __dmul_rn(Um[4 * r], s_T[cc]);
-                    s = __dadd_rn(s, __dmul_rn(Um[4 * r + 1], s_T[4 + cc]));
-                    s = __dadd_rn(s, __dmul_rn(Um[4 * r + 2], s_T[8 + cc]));
-                    s = __dadd_rn(s, __dmul_rn(Um[4 * r + 3], s_T[12 + cc]));
-                    Tn[4 * r + cc] = s;
-                }
-#pragma unroll
-            for (int k = 0; k < 16; ++k) { s_T[k] = Tn[k]; s_U[k] = Um[k]; }
         }
-        __syncthreads();
-        // P <- U * P
-        for (int i = tid; i < ns; i += kIcpThreads) {
-            double x = px[i], y = py[i], z = pz[i];
-            transform_point(s_U, true, x, y, z);
-            px[i] = x; py[i] = y; pz[i] = z;
-        }
-        __syncthreads();
-        correspond();
-        if (tid == 0) {
-            const double c = s_red[0][0];
-            const double fit = c > 0 ? c / (double)ns : 0.0;
-            const double rmse = c > 0 ? sqrt(s_red[0][1] / c) : 0.0;
-            s_stop = (fabs(s_prev[0] - fit) < p.rel_fit && fabs(s_prev[1] - rmse) < p.rel_rmse) ? 1 : 0;
-            s_prev[0] = fit;
-            s_prev[1] = rmse;
-        }
-        __syncthreads();
+        __syncthreads();  // barrier B
         iters = it + 1;
         if (s_stop) break;
     }
+    __syncthreads();
 
     // outputs: pose (cluster_icp.py:161-165), world cluster = T * S (:167), correspondences
     if (tid == 0) {
