@@ -37,6 +37,18 @@ int grow_dev(void **p, size_t *have, size_t need) {
     *have = need;
     return AURDF_OK;
 }
+// true when a host pointer is page-locked (cudaMallocHost / cudaHostRegister): it can be the
+// source or destination of an asynchronous copy without going through the staging buffer
+bool is_pinned(const void *p) {
+    if (!p) return false;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeHost;
+}
+
 int grow_pinned(void **p, size_t *have, size_t need) {
     if (need <= *have) return AURDF_OK;
     if (*p) cudaFreeHost(*p);
@@ -131,24 +143,44 @@ extern "C" int aurdf_icp_sweep_host(aurdf_ctx *c, const void *src_xyz, int pts_d
     if ((rc = grow_dev(&c->d_in, &c->d_in_bytes, in_bytes)) != AURDF_OK) return rc;
     if ((rc = grow_dev(&c->d_out, &c->d_out_bytes, out_bytes)) != AURDF_OK) return rc;
 
+    // host -> device: pinned caller buffers are copied straight from where they are; pageable
+    // ones are packed into the context's pinned staging buffer first
     char *hi = (char *)c->h_in;
-    if (n_src) memcpy(hi + o_src, src_xyz, (size_t)n_src * 3 * psz);
-    if (n_tgt) memcpy(hi + o_tgt, tgt_xyz, (size_t)n_tgt * 3 * psz);
-    if (n_box) memcpy(hi + o_box, box_xyz, (size_t)n_box * 3 * bsz);
-    memcpy(hi + o_soff, src_off, (size_t)(n_tiles + 1) * 4);
-    memcpy(hi + o_toff, tgt_off, (size_t)(n_frames + 1) * 4);
-    memcpy(hi + o_tf, tile_frame, (size_t)n_tiles * 4);
-    if (box_xyz) memcpy(hi + o_boff, box_off, (size_t)(n_tiles + 1) * 4);
-    memcpy(hi + o_init, init_T, (size_t)n_tiles * 16 * 8);
-    AURDF_CUDA_CHECK(cudaMemcpyAsync(c->d_in, c->h_in, in_bytes, cudaMemcpyHostToDevice, c->stream));
-    c->last_h2d = (int64_t)in_bytes;
+    char *di = (char *)c->d_in;
+    c->last_h2d = 0;
     c->last_d2h = 0;
+    auto h2d = [&](size_t off, const void *src, size_t bytes) -> int {
+        if (!bytes) return AURDF_OK;
+        const void *from = src;
+        if (!is_pinned(src)) {
+            memcpy(hi + off, src, bytes);
+            from = hi + off;
+        }
+        AURDF_CUDA_CHECK(cudaMemcpyAsync(di + off, from, bytes, cudaMemcpyHostToDevice, c->stream));
+        c->last_h2d += (int64_t)bytes;
+        return AURDF_OK;
+    };
+    if ((rc = h2d(o_src, src_xyz, (size_t)n_src * 3 * psz)) != AURDF_OK) return rc;
+    if ((rc = h2d(o_tgt, tgt_xyz, (size_t)n_tgt * 3 * psz)) != AURDF_OK) return rc;
+    if ((rc = h2d(o_box, box_xyz, (size_t)n_box * 3 * bsz)) != AURDF_OK) return rc;
+    if ((rc = h2d(o_soff, src_off, (size_t)(n_tiles + 1) * 4)) != AURDF_OK) return rc;
+    if ((rc = h2d(o_toff, tgt_off, (size_t)(n_frames + 1) * 4)) != AURDF_OK) return rc;
+    if ((rc = h2d(o_tf, tile_frame, (size_t)n_tiles * 4)) != AURDF_OK) return rc;
+    if (box_xyz && (rc = h2d(o_boff, box_off, (size_t)(n_tiles + 1) * 4)) != AURDF_OK) return rc;
+    if ((rc = h2d(o_init, init_T, (size_t)n_tiles * 16 * 8)) != AURDF_OK) return rc;
 
     int64_t cap = c->cap_hint > 0 ? c->cap_hint : 4 * n_src + 2 * (int64_t)n_tiles + 1024;
     if (cap > cap_upper) cap = cap_upper;
     if (cap < 2) cap = 2;
-    char *di = (char *)c->d_in, *d_o = (char *)c->d_out;
+    char *d_o = (char *)c->d_out;
     char *ho = (char *)c->h_out;
+    // device -> host targets: straight into pinned caller buffers, through staging otherwise
+    struct Out { void *dst; size_t off, bytes; bool direct; };
+    Out outs[7] = {{out_T, q_T, (size_t)n_tiles * 16 * 8, false},     {out_world_xyz, q_world, (size_t)n_src * 3 * 8, false},
+                   {out_corr, q_corr, (size_t)n_src * 4, false},       {out_fitness, q_fit, (size_t)n_tiles * 8, false},
+                   {out_rmse, q_rmse, (size_t)n_tiles * 8, false},     {out_iters, q_it, (size_t)n_tiles * 4, false},
+                   {out_ntgt, q_nt, (size_t)n_tiles * 4, false}};
+    for (Out &o_ : outs) o_.direct = o_.bytes && is_pinned(o_.dst);
     for (int attempt = 0; attempt < 2; ++attempt) {
         const size_t ws = aurdf_icp_workspace_bytes(n_tiles, n_src, cap);
         if ((rc = grow_dev(&c->d_ws, &c->d_ws_bytes, ws)) != AURDF_OK) return rc;
@@ -161,9 +193,17 @@ extern "C" int aurdf_icp_sweep_host(aurdf_ctx *c, const void *src_xyz, int pts_d
                              (double *)(d_o + q_fit), (double *)(d_o + q_rmse), (int32_t *)(d_o + q_it),
                              (int32_t *)(d_o + q_nt), c->d_ws, c->d_ws_bytes, cap, (int32_t *)(d_o + q_status), c->stream);
         if (rc != AURDF_OK) return rc;
-        AURDF_CUDA_CHECK(cudaMemcpyAsync(c->h_out, c->d_out, out_bytes, cudaMemcpyDeviceToHost, c->stream));
+        // optimistic: queue the status and every output behind the kernels, synchronise once;
+        // if the capacity guess was too small the copies are simply repeated after the re-run
+        AURDF_CUDA_CHECK(cudaMemcpyAsync(ho + q_status, d_o + q_status, 16, cudaMemcpyDeviceToHost, c->stream));
+        c->last_d2h += 16;
+        for (Out &o_ : outs) {
+            if (!o_.bytes) continue;
+            AURDF_CUDA_CHECK(cudaMemcpyAsync(o_.direct ? o_.dst : (void *)(ho + o_.off), d_o + o_.off, o_.bytes,
+                                             cudaMemcpyDeviceToHost, c->stream));
+            c->last_d2h += (int64_t)o_.bytes;
+        }
         AURDF_CUDA_CHECK(cudaStreamSynchronize(c->stream));
-        c->last_d2h += (int64_t)out_bytes;
         const int32_t *st = (const int32_t *)(ho + q_status);
         const int64_t need = (int64_t)(uint32_t)st[1] | ((int64_t)st[2] << 32);
         if (!st[0]) {
@@ -176,13 +216,9 @@ extern "C" int aurdf_icp_sweep_host(aurdf_ctx *c, const void *src_xyz, int pts_d
             return AURDF_ECAPACITY;
         }
         cap = need;
+        c->last_d2h = 0;
     }
-    memcpy(out_T, ho + q_T, (size_t)n_tiles * 16 * 8);
-    if (n_src) memcpy(out_world_xyz, ho + q_world, (size_t)n_src * 3 * 8);
-    if (n_src) memcpy(out_corr, ho + q_corr, (size_t)n_src * 4);
-    memcpy(out_fitness, ho + q_fit, (size_t)n_tiles * 8);
-    memcpy(out_rmse, ho + q_rmse, (size_t)n_tiles * 8);
-    memcpy(out_iters, ho + q_it, (size_t)n_tiles * 4);
-    memcpy(out_ntgt, ho + q_nt, (size_t)n_tiles * 4);
+    for (Out &o_ : outs)
+        if (o_.bytes && !o_.direct) memcpy(o_.dst, ho + o_.off, o_.bytes);
     return AURDF_OK;
 }

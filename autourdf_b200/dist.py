@@ -1,0 +1,85 @@
+"""Multi-GPU layer of the cluster-ICP sweep: one process per GPU (torch.distributed), tiles
+sharded by contiguous frame blocks, ONE all-gather of the fitted poses per sweep.
+
+Why it shards: the K cluster tiles of a frame are independent (the loop at reference
+PointCloud/cluster_icp.py:131 carries no state) and so are frames once their init poses are
+given; sequences are independent too (mlp_reg.py:434-435).  Nothing is exchanged on the data
+path; the only collective is the all-gather of (tiles x 16) float64 poses (+ fitness, rmse,
+iteration counts) so every rank ends the sweep holding all poses, as the single-process
+reference does.  Correspondences and world clusters stay sharded.
+
+The local compute is injected (``run_local``), so the partition / gather logic is exercised on
+CPU with gloo in tests/ and with the CUDA sweep + NCCL on the GPUs.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def frame_partition(batch, world: int):
+    """Contiguous frame ranges [f0, f1) per rank, balanced by the pair-evaluation estimate
+    sum(n_s * M) of each frame (keeps every target cloud on exactly one GPU)."""
+    F = batch.n_frames
+    ns = np.diff(batch.src_off).astype(np.float64)
+    M = np.diff(batch.tgt_off).astype(np.float64)
+    cost = np.zeros(F)
+    np.add.at(cost, batch.tile_frame, ns * M[batch.tile_frame])
+    cum = np.concatenate([[0.0], np.cumsum(cost)])
+    total = cum[-1]
+    cuts = [0]
+    for r in range(1, world):
+        target = total * r / world
+        f = int(np.searchsorted(cum, target, side="left"))
+        f = min(max(f, cuts[-1]), F)
+        cuts.append(f)
+    cuts.append(F)
+    return [(cuts[r], cuts[r + 1]) for r in range(world)]
+
+
+def sharded_sweep(batch, run_local, group=None, device="cpu"):
+    """Run ``run_local(sub_batch) -> dict(T (b,4,4), fitness, rmse, iters)`` on this rank's
+    frame block and all-gather the per-tile results.  Returns (gathered dict over ALL tiles in
+    the original tile order, this rank's local result dict, (f0, f1))."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    parts = frame_partition(batch, world)
+    f0, f1 = parts[rank]
+    sub = batch.frame_slice(f0, f1)
+    local = run_local(sub) if sub.n_tiles else dict(T=np.zeros((0, 4, 4)), fitness=np.zeros(0), rmse=np.zeros(0),
+                                                    iters=np.zeros(0, dtype=np.int32))
+    if world == 1:
+        return dict(T=np.asarray(local["T"]), fitness=np.asarray(local["fitness"]), rmse=np.asarray(local["rmse"]),
+                    iters=np.asarray(local["iters"])), local, (f0, f1)
+    # tiles per rank (frame-major tile order => each rank owns a contiguous tile range)
+    counts = [int(((batch.tile_frame >= a) & (batch.tile_frame < b)).sum()) for a, b in parts]
+    width = max(max(counts), 1)
+    # one padded (width, 19) float64 payload per rank: 16 pose entries + fitness + rmse + iters
+    pay = torch.zeros((width, 19), dtype=torch.float64, device=device)
+    n = counts[rank]
+    if n:
+        as_t = lambda a: torch.as_tensor(a, dtype=torch.float64, device=device)
+        pay[:n, :16] = as_t(local["T"]).reshape(n, 16)
+        pay[:n, 16] = as_t(local["fitness"])
+        pay[:n, 17] = as_t(local["rmse"])
+        pay[:n, 18] = as_t(local["iters"])
+    out = torch.empty((world * width, 19), dtype=torch.float64, device=device)   # concatenated layout
+    dist.all_gather_into_tensor(out, pay, group=group)
+    out = out.cpu().numpy().reshape(world, width, 19)
+    rows = np.concatenate([out[r, :counts[r]] for r in range(world)], axis=0)
+    return dict(T=rows[:, :16].reshape(-1, 4, 4).copy(), fitness=rows[:, 16].copy(), rmse=rows[:, 17].copy(),
+                iters=rows[:, 18].astype(np.int32)), local, (f0, f1)
+
+
+def cuda_run_local(device=None, **kw):
+    """``run_local`` backed by the CUDA sweep on this rank's GPU."""
+    from . import cluster_icp as ci
+
+    def run(sub):
+        d = ci.batch_to_device(sub, device=device or torch.device("cuda", torch.cuda.current_device()))
+        r = ci.icp_sweep(d["src"], d["src_off"], d["tgt"], d["tgt_off"], d["tile_frame"], d["box"], d["box_off"],
+                         d["init_T"], max_src_per_tile=int(np.diff(sub.src_off).max()), **kw)
+        return dict(T=r.T, fitness=r.fitness, rmse=r.rmse, iters=r.iters, corr=r.corr, world=r.world, ntgt=r.ntgt)
+
+    return run

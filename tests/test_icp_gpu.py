@@ -159,3 +159,43 @@ def test_permutation_invariance(synth):
         assert np.array_equal(c0 >= 0, c1 >= 0)
         assert np.array_equal(perms[f][c1[ok]], c0[ok])
     assert np.abs(g0["T"] - g1["T"]).max() <= 1e-9
+
+
+def _shard_worker(rank, world, port, q):
+    import sys
+    ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)   # 2 ranks share the one GPU of the test box
+    try:
+        from autourdf_b200 import synth
+        from autourdf_b200.dist import cuda_run_local, sharded_sweep
+        torch.cuda.set_device(0)
+        b = synth.make_config("wx200")
+        run = cuda_run_local(torch.device("cuda", 0))
+        allr, local, _ = sharded_sweep(b, run, device="cpu")
+        full = run(b)
+        ok = (np.array_equal(allr["T"], full["T"].cpu().numpy()) and
+              np.array_equal(allr["iters"], full["iters"].cpu().numpy()))
+        q.put((rank, bool(ok), ""))
+    except Exception as e:
+        q.put((rank, False, repr(e)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_two_ranks_bit_identical_to_single():
+    """the sharded result must be bit-identical to the 1-GPU result"""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29600 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_shard_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=240) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(r[1] for r in res), res
