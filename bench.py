@@ -50,6 +50,23 @@ def load_peaks():
     return 6650.0, "fallback"
 
 
+def load_traffic(kernel="icp_tiles_kernel"):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of `kernel`, from the newest
+    committed ncu --set full summary (profiles/*_kernels.json, written by profiles/summarize.py)."""
+    import glob
+    mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "*_kernels.json")), reverse=True):
+        try:
+            for k in json.load(open(path)):
+                if k["kernel"].endswith(kernel):
+                    rd = k["dram__bytes_read.sum"] * mult[k["dram__bytes_read.sum__unit"]]
+                    wr = k["dram__bytes_write.sum"] * mult[k["dram__bytes_write.sum__unit"]]
+                    return rd + wr, os.path.basename(path)
+        except Exception:
+            continue
+    return None, None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)"""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
@@ -300,8 +317,10 @@ def main():
         sm_hz = (clocks.get("sm_mhz") or 1965.0) * 1e6
         fp64_peak = 148 * 64 * sm_hz                               # FP64 lane-instr/s (64 lanes/clk/SM)
         fp64_rate = 9.0 * pairs / (k_ms * 1e-3)                    # 3 sub + 3 mul + 2 add + 1 compare per pair
+        traffic, traffic_src = load_traffic()
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": None, "peak_source": peak_src, "kernel": "icp_tiles_kernel",
+                    "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                    "kernel": "icp_tiles_kernel",
                     "kernel_ms": k_ms, "kernel_share_of_step": kms.value / dev_ms,
                     "algorithmic_bytes_per_launch": b_alg,
                     "binding_roof": {"bound": "fp64_issue", "pair_evals_per_launch": pairs,
