@@ -27,7 +27,7 @@
 
 namespace aurdf {
 
-constexpr int kIcpThreads = 128;
+constexpr int kIcpThreads = 256;
 constexpr int kIcpWarps = kIcpThreads / 32;
 constexpr int kQChunk = 512;      // target points staged per shared-memory chunk (12 KB as f64 SoA)
 constexpr int kPSmemMax = 2048;   // most source points a tile may keep in shared memory
@@ -436,6 +436,17 @@ __device__ __forceinline__ double fast_rcp(double x) {
     return y;
 }
 
+// 1/x to ~1 ulp: MUFU.RCP64H seed + two Newton steps (a true division is ~25 dependent
+// instructions; this is ~6).
+__device__ __forceinline__ double rcp_nr2(double x) {
+    if (!(fabs(x) > 1e-290 && fabs(x) < 1e290)) return 1.0 / x;
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    y = y * (2.0 - x * y);
+    y = y + y * (1.0 - x * y);
+    return y;
+}
+
 // Kabsch rotation for the common case, written for a short dependent chain (this is the
 // serial section of every ICP iteration).  The source points are re-posed every iteration, so
 // the optimal rotation R = argmax tr(R^T sigma) is near the identity.  R is optimal and proper
@@ -482,7 +493,7 @@ __device__ bool kabsch_rotation_newton(const double (&sigma)[3][3], double (&R)[
         const double vv = vx * vx + vy * vy + vz * vz;
         if (!(vv < 1.0)) return false;  // more than 90 degrees in one step: not the near-identity case
         // Cayley: E = ((1 - vv) I + 2 v v^T + 2 [v]x) / (1 + vv), an exact rotation
-        const double rden = 1.0 / (1.0 + vv);
+        const double rden = rcp_nr2(1.0 + vv);
         const double a = (1.0 - vv) * rden, b2 = 2.0 * rden;
         double E[3][3];
         E[0][0] = a + b2 * vx * vx; E[0][1] = b2 * (vx * vy - vz); E[0][2] = b2 * (vx * vz + vy);
@@ -503,8 +514,8 @@ __device__ bool kabsch_rotation_newton(const double (&sigma)[3][3], double (&R)[
                 A[i][j] = An[i][j];
                 R[i][j] = Rn[i][j];
             }
-        // quadratic convergence: a step of |v| < 3e-9 leaves an error of ~|v|^2, below rounding
-        if (vv < 1e-17) {
+        // quadratic convergence: a step of |v| < 1e-7 leaves an error of ~|v|^2 <= 1e-14
+        if (vv < 1e-14) {
             converged = true;
             break;
         }
@@ -542,6 +553,7 @@ struct IcpParams {
     int *out_corr;
     double *out_fit, *out_rmse;
     int *out_iters, *out_ntgt;
+    long long *dbg_clock;  // optional: per-phase cycle stamps of tile 0 (debug builds of the bench only)
 };
 
 // x' = ((m0 x + m1 y) + m2 z) + m3, each operation rounded (open3d PointCloud::Transform)
@@ -584,13 +596,14 @@ __device__ __forceinline__ void warp_sum16(double (&v)[16], int lane) {
 //   warp 1    lane 0: fitness, rmse and open3d's convergence test          -> stop flag
 //   barrier B
 //   warp 3    16 lanes: T <- U T (off the critical path, overlaps the next pass)
-__global__ void __launch_bounds__(kIcpThreads, 5)
+__global__ void __launch_bounds__(kIcpThreads, 2)
 icp_tiles_kernel(const IcpParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *sqx = reinterpret_cast<double *>(smem_raw);
     double *sqy = sqx + kQChunk;
     double *sqz = sqy + kQChunk;
-    double *spx_s = sqz + kQChunk;
+    float4 *sqf = reinterpret_cast<float4 *>(sqz + kQChunk);  // float32 copy (x,y,z about the tile origin)
+    double *spx_s = reinterpret_cast<double *>(sqf + kQChunk);
     double *spy_s = spx_s + p.p_cap;
     double *spz_s = spy_s + p.p_cap;
     int *scj_s = reinterpret_cast<int *>(spz_s + p.p_cap);
@@ -603,6 +616,7 @@ icp_tiles_kernel(const IcpParams p) {
     __shared__ double s_prev[2];              // fitness, rmse of the previous pass
     __shared__ double s_warm[18];             // singular vectors of the previous fit
     __shared__ int s_stop;
+    __shared__ float s_amax[kIcpWarps];       // max |target coordinate - origin| per warp
     __shared__ __align__(8) uint64_t s_bar;
 
     if (p.status_int[0]) return;  // compacted-target capacity exceeded: leave outputs untouched
@@ -675,6 +689,30 @@ icp_tiles_kernel(const IcpParams p) {
     const double ox = nt > 0 ? __ldg(p.qx + q0) : 0.0, oy = nt > 0 ? __ldg(p.qy + q0) : 0.0,
                  oz = nt > 0 ? __ldg(p.qz + q0) : 0.0;
 
+    // float32 pre-filter (resident tiles): targets about the origin, rounded to float32, and the
+    // largest coordinate magnitude A_q, which scales the rounding-error bound of the filter
+    const bool use_f32 = resident && nt > 0;
+    float aq = 0.f;
+    if (use_f32) {
+        float amax = 0.f;
+        for (int j = tid; j < nt; j += kIcpThreads) {
+            const float fx = (float)(sqx[j] - ox), fy = (float)(sqy[j] - oy), fz = (float)(sqz[j] - oz);
+            sqf[j] = make_float4(fx, fy, fz, 0.f);
+            amax = fmaxf(amax, fmaxf(fabsf(fx), fmaxf(fabsf(fy), fabsf(fz))));
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+        if (lane == 0) s_amax[warp] = amax;
+        __syncthreads();
+#pragma unroll
+        for (int w = 0; w < kIcpWarps; ++w) aq = fmaxf(aq, s_amax[w]);
+    }
+
+    long long dbg_n = 0;
+    auto stamp = [&]() {
+        if (p.dbg_clock && b == 0 && tid == 0 && dbg_n < 4096) p.dbg_clock[dbg_n++] = clock64();
+    };
+
     // One correspondence pass.  apply: first move the points by the current update s_U.
     // Leaves per-warp partial sums in s_part / s_cnt (valid after the next barrier).
     auto pass = [&](bool apply) {
@@ -694,24 +732,89 @@ icp_tiles_kernel(const IcpParams p) {
                 if (S > 1) __syncwarp();  // the S lanes of a point have all read the old value
                 if (active && sub == 0) { px[i] = x; py[i] = y; pz[i] = z; }
             }
+            if (apply) stamp();  // [+1] P update done
             double bd = INFINITY;
             int bj = -1;
-            for (int c = 0; c < nchunks; ++c) {
+            // ---- float32 pre-filter: best and second-best float32 distance of this point.  If the
+            // gap exceeds twice the worst-case float32 error the float32 winner is provably the
+            // float64 argmin and only its exact distance is evaluated; otherwise the point takes
+            // the exact scan below (probability ~1e-3 per point).
+            bool need_exact = active;
+            if (use_f32) {
+                float m1 = INFINITY, m2 = INFINITY;
+                int j1 = -1;
+                float fx = 0.f, fy = 0.f, fz = 0.f;
+                if (active) {
+                    fx = (float)(x - ox); fy = (float)(y - oy); fz = (float)(z - oz);
+#pragma unroll 4
+                    for (int j = sub; j < nt; j += S) {
+                        const float4 q = sqf[j];
+                        const float dx = fx - q.x, dy = fy - q.y, dz = fz - q.z;
+                        const float d = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+                        m2 = fminf(m2, fmaxf(m1, d));
+                        j1 = d < m1 ? j : j1;
+                        m1 = fminf(m1, d);
+                    }
+                }
+                for (int o = S >> 1; o > 0; o >>= 1) {
+                    const float om1 = __shfl_xor_sync(0xffffffffu, m1, o), om2 = __shfl_xor_sync(0xffffffffu, m2, o);
+                    const int oj1 = __shfl_xor_sync(0xffffffffu, j1, o);
+                    m2 = fminf(fminf(m2, om2), fmaxf(m1, om1));
+                    if (om1 < m1 || (om1 == m1 && oj1 >= 0 && (j1 < 0 || oj1 < j1))) { m1 = om1; j1 = oj1; }
+                }
+                if (active && j1 >= 0) {
+                    // |d32 - d_true| <= 3.01u(R + 2 sqrt3 dl sqrtR + 3 dl^2) + 2 sqrt3 dl sqrtR + 3 dl^2 with
+                    // u = 2^-24 and dl <= 4 u max(A_q, |a|) the per-coordinate error of a float32 difference;
+                    // tau over-covers that by more than 4x
+                    const float u = 5.9604645e-8f;
+                    const float amag = fmaxf(aq, fmaxf(fabsf(fx), fmaxf(fabsf(fy), fabsf(fz))));
+                    const float dl = 4.f * u * amag;
+                    const float tau = 16.f * (dl * sqrtf(m2) * 1.001f + dl * dl + u * m2);
+                    if (nt == 1 || (m2 - m1 > 2.f * tau && m2 < INFINITY)) {
+                        need_exact = false;
+                        if (sub == 0) {
+                            const double dx = __dsub_rn(x, sqx[j1]), dy = __dsub_rn(y, sqy[j1]), dz = __dsub_rn(z, sqz[j1]);
+                            bd = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+                            bj = j1;
+                        }
+                    }
+                }
+            }
+            // (streamed tiles always walk the chunks: the loop holds block barriers)
+            const bool warp_scans = !resident || __any_sync(0xffffffffu, need_exact);
+            for (int c = 0; warp_scans && c < nchunks; ++c) {
                 if (!resident) {
                     __syncthreads();  // everyone done with the previous chunk
                     load_chunk(c);
                 }
                 const int n = min(kQChunk, nt - c * kQChunk);
                 const int jbase = c * kQChunk;
-                if (active) {
-#pragma unroll 4
-                    for (int j = sub; j < n; j += S) {
+                if (need_exact) {
+                    // four independent distance chains per trip, merged by a min-tree (lower index
+                    // wins ties at every node, as a sequential strict '<' scan would): the only
+                    // loop-carried dependency is one compare per four targets
+                    auto dist2 = [&](int j) {
                         const double dx = __dsub_rn(x, sqx[j]), dy = __dsub_rn(y, sqy[j]), dz = __dsub_rn(z, sqz[j]);
-                        const double d = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+                        return __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+                    };
+                    int j = sub;
+                    for (; j + 3 * S < n; j += 4 * S) {
+                        const double d0 = dist2(j), d1 = dist2(j + S), d2 = dist2(j + 2 * S), d3 = dist2(j + 3 * S);
+                        const bool p01 = d1 < d0, p23 = d3 < d2;
+                        const double m01 = p01 ? d1 : d0, m23 = p23 ? d3 : d2;
+                        const int j01 = p01 ? j + S : j, j23 = p23 ? j + 3 * S : j + 2 * S;
+                        const bool pm = m23 < m01;
+                        const double m = pm ? m23 : m01;
+                        const int jm = pm ? j23 : j01;
+                        if (m < bd) { bd = m; bj = jbase + jm; }
+                    }
+                    for (; j < n; j += S) {
+                        const double d = dist2(j);
                         if (d < bd) { bd = d; bj = jbase + j; }
                     }
                 }
             }
+            if (apply) stamp();  // [+2] NN scan done
             // (d, j) lexicographic min across the S lanes of this point
             for (int o = S >> 1; o > 0; o >>= 1) {
                 const double od = __shfl_xor_sync(0xffffffffu, bd, o);
@@ -735,6 +838,7 @@ icp_tiles_kernel(const IcpParams p) {
                 acc[13] += bz * ax; acc[14] += bz * ay; acc[15] += bz * az;
             }
         }
+        if (apply) stamp();  // [+3] merge + moment accumulation done
         warp_sum16(acc, lane);
         if ((lane & 1) == 0) s_part[warp][lane >> 1] = acc[0];
         if (lane == 0) s_cnt[warp] = cnt;
@@ -761,7 +865,7 @@ icp_tiles_kernel(const IcpParams p) {
         const double *t = s_tot[0];
         double Um[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
         if (c > 0) {
-            const double inv = 1.0 / (double)c;
+            const double inv = rcp_nr2((double)c);
             const double ma[3] = {t[1] * inv, t[2] * inv, t[3] * inv};
             const double mb[3] = {t[4] * inv, t[5] * inv, t[6] * inv};
             double sigma[3][3], R[3][3];
@@ -799,6 +903,7 @@ icp_tiles_kernel(const IcpParams p) {
         if (lane < 16) s_T[lane] = v;
     };
 
+    stamp();
     pass(false);
     __syncthreads();  // barrier A
     if (warp == 0) {
@@ -815,14 +920,18 @@ icp_tiles_kernel(const IcpParams p) {
 
     int iters = 0;
     for (int it = 0; it < p.max_iter; ++it) {
+        stamp();  // [4k+0] iteration start
         if (warp == kIcpWarps - 1) compose_pose();  // uses s_U of this iteration; next write is after barrier A
         pass(true);
+        stamp();  // [4k+1] pass done (warp 0)
         __syncthreads();  // barrier A
+        stamp();  // [4k+2] barrier A passed
         if (warp == 0) {
             // speculative: the fit for iteration it+1 runs while warp 1 decides whether to stop
             const int c = totals(0);
             if (lane == 0 && it + 1 < p.max_iter) fit_pose(c);
-        } else if (warp == 1) {
+        }
+        else if (warp == 1) {
             const int c = totals(1);
             if (lane == 0) {
                 const double fit = c > 0 ? (double)c / (double)ns : 0.0;
@@ -832,6 +941,7 @@ icp_tiles_kernel(const IcpParams p) {
                 s_prev[1] = rmse;
             }
         }
+        stamp();  // [4k+3] fit done
         __syncthreads();  // barrier B
         iters = it + 1;
         if (s_stop) break;
@@ -875,6 +985,9 @@ extern "C" size_t aurdf_icp_workspace_bytes(int32_t n_tiles, int64_t total_src_p
     if (n_tiles < 0 || total_src_points < 0 || tgt_capacity < 0) return 0;
     return make_layout(n_tiles, total_src_points, tgt_capacity).total;
 }
+
+static long long *g_dbg_clock = nullptr;
+extern "C" __attribute__((visibility("default"))) void aurdf_debug_set_clock_buffer(void *p) { g_dbg_clock = (long long *)p; }
 
 extern "C" int aurdf_icp_sweep_launches(void) { return 4; }
 
@@ -950,7 +1063,8 @@ extern "C" int aurdf_icp_sweep(const void *src_xyz, int pts_dtype, const int32_t
     int p_cap = max_src_per_tile > 0 ? max_src_per_tile : 256;
     if (p_cap > kPSmemMax) p_cap = kPSmemMax;
     p_cap = (p_cap + 1) & ~1;
-    const size_t smem = (size_t)3 * kQChunk * sizeof(double) + (size_t)3 * p_cap * sizeof(double) + (size_t)p_cap * sizeof(int);
+    const size_t smem = (size_t)3 * kQChunk * sizeof(double) + (size_t)kQChunk * sizeof(float4) +
+                        (size_t)3 * p_cap * sizeof(double) + (size_t)p_cap * sizeof(int);
     if (smem > 48 * 1024)
         AURDF_CUDA_CHECK(cudaFuncSetAttribute(icp_tiles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 
@@ -967,6 +1081,7 @@ extern "C" int aurdf_icp_sweep(const void *src_xyz, int pts_dtype, const int32_t
     P.pspill = pspill; P.p_cap = p_cap;
     P.out_T = out_T; P.out_world = out_world_xyz; P.out_corr = out_corr; P.out_fit = out_fitness;
     P.out_rmse = out_rmse; P.out_iters = out_iters; P.out_ntgt = out_ntgt;
+    P.dbg_clock = g_dbg_clock;
     EvPair ev{nullptr, nullptr};
     if (g_prof_on) {
         AURDF_CUDA_CHECK(cudaEventCreate(&ev.a));

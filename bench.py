@@ -32,6 +32,9 @@ import time
 
 import numpy as np
 
+# one JSON line on stdout: keep NCCL's version banner out of it
+os.environ["NCCL_DEBUG"] = os.environ.get("AURDF_NCCL_DEBUG", "WARN")
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
@@ -140,7 +143,7 @@ def cpu_modes(O, b, budget_s=4.0):
                           correspondence search on every host thread (open3d's own structure)
       tile_parallel       OpenMP over tiles on every host thread -- NOT the reference's structure,
                           the strongest CPU port we could write; reported for context."""
-    cores = O.lib().orc_max_threads()
+    cores = O.use_all_host_threads()
     out = {}
     O.set_reference_threading(False)
     t, r = _time(lambda: cpu_sweep(O, b, 1), 2, budget_s)

@@ -630,6 +630,15 @@ ORC_API int orc_masked_icp_sweep(const double *src, const int *src_off, const do
     return status;
 }
 
+/* torchrun exports OMP_NUM_THREADS=1; the CPU baseline sets the thread count explicitly */
+ORC_API void orc_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 ORC_API int orc_max_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

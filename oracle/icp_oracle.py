@@ -53,6 +53,7 @@ def lib():
         L.orc_masked_icp_sweep.restype = C.c_int
         L.orc_max_threads.restype = C.c_int
         L.orc_set_reference_threading.argtypes = [C.c_int]
+        L.orc_set_num_threads.argtypes = [C.c_int]
         _LIB = L
     return _LIB
 
@@ -61,6 +62,13 @@ def set_reference_threading(on: bool):
     """True: tiles serial, OpenMP inside the correspondence search (open3d's own structure);
     False (default): OpenMP over tiles, deterministic per-tile arithmetic."""
     lib().orc_set_reference_threading(int(bool(on)))
+
+
+def use_all_host_threads() -> int:
+    """OpenMP thread count := CPUs this process may run on (torchrun exports OMP_NUM_THREADS=1)"""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    lib().orc_set_num_threads(n)
+    return n
 
 
 def _d(a):

@@ -41,8 +41,10 @@ def assert_parity(g, o, pose_tol=1e-5, what="", batch=None):
         keep[ill] = False
         for t in ill:
             pkeep[batch.src_off[t]:batch.src_off[t + 1]] = False
-            R, Ro = g["T"][t][:3, :3], o["T"][t][:3, :3]      # still as rigid as the oracle's
-            assert np.abs(R @ R.T - np.eye(3)).max() <= np.abs(Ro @ Ro.T - np.eye(3)).max() + 1e-9
+            # still as rigid as the oracle's (the float32-valued init pose is itself only
+            # orthogonal to ~1e-7, and U @ T0 inherits a U-dependent share of that)
+            R, Ro = g["T"][t][:3, :3], o["T"][t][:3, :3]
+            assert np.abs(R @ R.T - np.eye(3)).max() <= 4 * np.abs(Ro @ Ro.T - np.eye(3)).max() + 1e-9
             assert np.isfinite(g["T"][t]).all()
     bad = np.nonzero((g["corr"] != o["corr"]) & pkeep)[0]
     assert bad.size == 0, f"{what}: {bad.size} correspondence indices differ, first at {bad[:5]}"
