@@ -34,6 +34,9 @@ SIGNATURES = {
                                        _f64, _f64, _i32, _f64, _f64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "aurdf_ctx_last_copy_bytes": (None, [_vp, C.POINTER(_i64), C.POINTER(_i64)]),
     "aurdf_nn_l2": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, _i32, _i64, _vp, _vp, _vp]),
+    "aurdf_nn_f32_workspace_bytes": (_sz, [_i64]),
+    "aurdf_nn_f32": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i64, _i64, C.c_int, _vp, _vp, _vp, _sz, _vp]),
+    "aurdf_nn_f32_bwd": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i64, C.c_int, _vp, _vp, _vp]),
     "aurdf_se3_apply": (C.c_int, [_vp, _vp, _vp, _i32, _i64, C.c_int, _vp, _vp]),
     "aurdf_se3_apply_bwd": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i64, C.c_int, _vp, _vp, _vp]),
     "aurdf_se3_to_local": (C.c_int, [_vp, _vp, _vp, _i32, _i64, _vp, _vp]),

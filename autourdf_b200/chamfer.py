@@ -1,0 +1,94 @@
+"""Chamfer distance on the B200: drop-in for ``pytorch3d.loss.chamfer_distance`` as the reference
+uses it (``chamfer_distance(pred, y, norm=1)``, PointCloud/mlp_reg.py:96 inside the 300-epoch
+``train`` loop, and Sim/evaluation.py:81) -- SURVEY.md section 8(f)-1.
+
+Both nearest-neighbour directions run on the float32 brute-force kernel ``aurdf_nn_f32`` (split
+over query blocks AND target slices, merged by a packed 64-bit atomicMin); the backward is
+pytorch3d's ``knn_points`` backward (``aurdf_nn_f32_bwd``).  Differentiable in ``x`` and ``y``.
+Supported subset of pytorch3d's signature: ``norm`` 1 or 2, ``batch_reduction`` / ``point_reduction``
+in {"mean", "sum"}, optional lengths; normals / weights / single_directional are not used by the
+reference and raise NotImplementedError.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+
+
+def _offsets(lengths, P, N, device):
+    if lengths is None:
+        return torch.arange(0, (N + 1) * P, P, dtype=torch.int32, device=device), None
+    off = torch.zeros(N + 1, dtype=torch.int32, device=device)
+    off[1:] = torch.cumsum(lengths.to(torch.int32), 0)
+    return off, lengths
+
+
+def knn1(query, q_off, target, t_off, norm=1):
+    """packed 1-NN: query (Q,3) / target (T,3) float32 CUDA, int32 offsets (G+1,) -> (idx int32 (Q,),
+    dist float32 (Q,)); idx is relative to the group's target range."""
+    L = _lib.lib()
+    assert query.is_cuda and query.dtype == torch.float32 and target.dtype == torch.float32
+    query, target = query.contiguous(), target.contiguous()
+    Q, T, G = query.shape[0], target.shape[0], q_off.numel() - 1
+    idx = torch.empty(Q, dtype=torch.int32, device=query.device)
+    dist = torch.empty(Q, dtype=torch.float32, device=query.device)
+    ws = torch.empty(max(L.aurdf_nn_f32_workspace_bytes(Q), 8), dtype=torch.uint8, device=query.device)
+    _lib.check(L.aurdf_nn_f32(_lib.ptr(query), _lib.ptr(q_off), _lib.ptr(target), _lib.ptr(t_off), G, Q, T, int(norm),
+                              _lib.ptr(idx), _lib.ptr(dist), _lib.ptr(ws), ws.numel(), _lib.current_stream()), "aurdf_nn_f32")
+    return idx, dist
+
+
+class _Knn1(torch.autograd.Function):
+    """dist[i] = d(p1_i, p2_nn(i)) with pytorch3d's knn_points backward"""
+
+    @staticmethod
+    def forward(ctx, p1, off1, p2, off2, norm):
+        idx, dist = knn1(p1, off1, p2, off2, norm)
+        ctx.save_for_backward(p1, off1, p2, off2, idx)
+        ctx.norm = norm
+        ctx.mark_non_differentiable(idx)
+        return dist, idx
+
+    @staticmethod
+    def backward(ctx, gdist, _gidx):
+        p1, off1, p2, off2, idx = ctx.saved_tensors
+        L = _lib.lib()
+        g1 = torch.zeros_like(p1) if ctx.needs_input_grad[0] else None
+        g2 = torch.zeros_like(p2) if ctx.needs_input_grad[2] else None
+        gdist = gdist.contiguous().to(torch.float32)
+        _lib.check(L.aurdf_nn_f32_bwd(_lib.ptr(p1), _lib.ptr(off1), _lib.ptr(p2), _lib.ptr(off2), _lib.ptr(idx),
+                                      _lib.ptr(gdist), off1.numel() - 1, p1.shape[0], ctx.norm, _lib.ptr(g1), _lib.ptr(g2),
+                                      _lib.current_stream()), "aurdf_nn_f32_bwd")
+        return g1, None, g2, None, None
+
+
+def chamfer_distance(x, y, x_lengths=None, y_lengths=None, x_normals=None, y_normals=None, weights=None,
+                     batch_reduction="mean", point_reduction="mean", norm: int = 2, single_directional=False,
+                     abs_cosine=True):
+    """pytorch3d signature; x (N,P1,3), y (N,P2,3) float32 CUDA tensors -> (loss, None)."""
+    if x_normals is not None or y_normals is not None or weights is not None or single_directional:
+        raise NotImplementedError("normals / weights / single_directional are not on the reference's path")
+    if norm not in (1, 2):
+        raise ValueError("Support for 1 or 2 norm.")
+    if batch_reduction not in ("mean", "sum") or point_reduction not in ("mean", "sum"):
+        raise NotImplementedError("reductions other than mean / sum")
+    assert x.dim() == 3 and y.dim() == 3 and x.shape[0] == y.shape[0] and x.shape[2] == 3 and y.shape[2] == 3
+    N, P1, P2 = x.shape[0], x.shape[1], y.shape[1]
+    if x_lengths is not None or y_lengths is not None:
+        raise NotImplementedError("ragged batches: use knn1 with explicit offsets")
+    xo, _ = _offsets(None, P1, N, x.device)
+    yo, _ = _offsets(None, P2, N, x.device)
+    xf = x.reshape(N * P1, 3).to(torch.float32)
+    yf = y.reshape(N * P2, 3).to(torch.float32)
+    dx, _ = _Knn1.apply(xf, xo, yf, yo, norm)
+    dy, _ = _Knn1.apply(yf, yo, xf, xo, norm)
+    cham_x = dx.reshape(N, P1).sum(1)
+    cham_y = dy.reshape(N, P2).sum(1)
+    if point_reduction == "mean":
+        cham_x = cham_x / max(P1, 1)
+        cham_y = cham_y / max(P2, 1)
+    cham_x, cham_y = cham_x.sum(), cham_y.sum()
+    if batch_reduction == "mean":
+        cham_x, cham_y = cham_x / max(N, 1), cham_y / max(N, 1)
+    return cham_x + cham_y, None

@@ -137,6 +137,25 @@ AURDF_API int aurdf_nn_l2(const void *query_xyz, const int32_t *query_off, const
                 int32_t *out_idx, double *out_d2, aurdf_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------
+ * float32 1-NN under L1 (norm 1) or squared L2 (norm 2): pytorch3d 0.7.7 ops.knn_points(K=1), the
+ * operator inside loss.chamfer_distance(pred, y, norm=1) at PointCloud/mlp_reg.py:96 and
+ * Sim/evaluation.py:81.  Distances accumulate in pytorch3d's order, the first
+ * minimum wins.  out_idx is relative to the group's target range (-1 for an empty one).
+ * aurdf_nn_f32_bwd is knn_points' backward: grad_p1[i] += g_i * d dist/d p1, grad_p2[idx[i]] -= the
+ * same (atomic scatter; both gradient buffers must be zero-initialised by the caller, either may
+ * be NULL).  workspace: aurdf_nn_f32_workspace_bytes(n_queries) bytes, 8-byte aligned.
+ * ------------------------------------------------------------------------------------- */
+AURDF_API size_t aurdf_nn_f32_workspace_bytes(int64_t n_queries);
+AURDF_API int aurdf_nn_f32(const float *query_xyz, const int32_t *query_off, const float *target_xyz,
+                           const int32_t *target_off, int32_t n_groups, int64_t n_queries,
+                           int64_t n_targets, int norm, int32_t *out_idx, float *out_dist,
+                           void *workspace, size_t workspace_bytes, aurdf_stream_t stream);
+AURDF_API int aurdf_nn_f32_bwd(const float *p1_xyz, const int32_t *p1_off, const float *p2_xyz,
+                               const int32_t *p2_off, const int32_t *idx, const float *grad_dist,
+                               int32_t n_groups, int64_t n_p1, int norm, float *grad_p1,
+                               float *grad_p2, aurdf_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
  * SE(3) apply: calculate_pc(), PointCloud/mlp_reg.py:155-170:  out = X @ R_k^T + t_k for
  * every point of group k (dtype F32 or F64 for points, poses and output alike).
  * aurdf_se3_apply_bwd is its adjoint for autograd: grad_X = g R_k, grad_T[k][:3,:3] =
