@@ -40,6 +40,7 @@ SIGNATURES = {
     "aurdf_se3_apply": (C.c_int, [_vp, _vp, _vp, _i32, _i64, C.c_int, _vp, _vp]),
     "aurdf_se3_apply_bwd": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i64, C.c_int, _vp, _vp, _vp]),
     "aurdf_se3_to_local": (C.c_int, [_vp, _vp, _vp, _i32, _i64, _vp, _vp]),
+    "aurdf_resample_clusters": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _f64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "aurdf_dq_op": (C.c_int, [C.c_int, _vp, _vp, _vp, _vp, _i64, C.c_int, _vp]),
 }
 

@@ -2,6 +2,7 @@
 #pragma once
 
 #include <cuda_runtime.h>
+#include <math.h>
 #include <stdint.h>
 
 #include "aurdf.h"
@@ -86,5 +87,49 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u
                  "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+
+// general 4x4 inverse, Gauss-Jordan with partial pivoting (np.linalg.inv stand-in)
+__device__ inline bool inv4(const double *A, double *Ai) {
+    double M[4][8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            M[i][j] = A[4 * i + j];
+            M[i][j + 4] = (i == j) ? 1.0 : 0.0;
+        }
+    bool ok = true;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        int piv = c;
+#pragma unroll
+        for (int r = c + 1; r < 4; ++r)
+            if (fabs(M[r][c]) > fabs(M[piv][c])) piv = r;
+        if (M[piv][c] == 0.0) ok = false;
+        if (piv != c) {
+            for (int j = 0; j < 8; ++j) {
+                const double t = M[c][j];
+                M[c][j] = M[piv][j];
+                M[piv][j] = t;
+            }
+        }
+        const double d = M[c][c];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) M[c][j] /= d;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            if (r == c) continue;
+            const double f = M[r][c];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) M[r][j] -= f * M[c][j];
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) Ai[4 * i + j] = M[i][j + 4];
+    return ok;
+}
+
 
 }  // namespace aurdf

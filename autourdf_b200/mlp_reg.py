@@ -84,3 +84,40 @@ def to_local(points_list, matrices):
     o = out.cpu().numpy()
     cuts = np.cumsum(sizes)[:-1]
     return [a.copy() for a in np.split(o, cuts)]
+
+
+def resample_cluster(segments, idx, n_clusters, matrices, normal=False, visual=False, _details=None):
+    """Reference signature (mlp_reg.py:172): ``segments`` is the reference's ``Segments`` object
+    (its ``pc_list[idx].points`` is the frame cloud) or directly an (N,3) array.  Seeded Lloyd
+    k-means + move into local frames, all on the GPU (``aurdf_resample_clusters``).  Returns the
+    list of (n_k,3) float64 clusters in their local frames.  ``normal=True`` needs open3d normal
+    estimation and is not on this path; ``visual`` is accepted and ignored."""
+    if normal:
+        raise NotImplementedError("normal=True (open3d normal estimation) is outside the accelerated path")
+    if hasattr(segments, "pc_list"):
+        pc_np = np.asarray(segments.pc_list[idx].points)
+    else:
+        pc_np = np.asarray(segments)
+    pc_np = np.ascontiguousarray(pc_np, dtype=np.float64).reshape(-1, 3)
+    mats = np.ascontiguousarray(np.asarray(matrices, dtype=np.float64)[:n_clusters].reshape(n_clusters, 4, 4))
+    L = _lib.lib()
+    dev = torch.device("cuda")
+    N = pc_np.shape[0]
+    cloud = torch.from_numpy(pc_np).to(dev)
+    off = torch.tensor([0, N], dtype=torch.int32, device=dev)
+    labels = torch.empty(N, dtype=torch.int32, device=dev)
+    centers = torch.empty((n_clusters, 3), dtype=torch.float64, device=dev)
+    local = torch.empty((N, 3), dtype=torch.float64, device=dev)
+    loff = torch.empty(n_clusters + 1, dtype=torch.int32, device=dev)
+    nit = torch.empty(1, dtype=torch.int32, device=dev)
+    inertia = torch.empty(1, dtype=torch.float64, device=dev)
+    _lib.check(L.aurdf_resample_clusters(_lib.ptr(cloud), _lib.ptr(off), _lib.ptr(torch.from_numpy(mats).to(dev)), 1,
+                                         n_clusters, N, 300, 1e-4, _lib.ptr(labels), _lib.ptr(centers), _lib.ptr(local),
+                                         _lib.ptr(loff), _lib.ptr(nit), _lib.ptr(inertia), _lib.current_stream()),
+               "aurdf_resample_clusters")
+    lo = loff.cpu().numpy()
+    loc = local.cpu().numpy()
+    if _details is not None:
+        _details.update(labels=labels.cpu().numpy(), centers=centers.cpu().numpy(), n_iter=int(nit.item()),
+                        inertia=float(inertia.item()))
+    return [loc[lo[k]:lo[k + 1]].copy() for k in range(n_clusters)]

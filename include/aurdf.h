@@ -173,6 +173,23 @@ AURDF_API int aurdf_se3_to_local(const double *xyz, const int32_t *off, const do
                        int64_t n_points, double *out_xyz, aurdf_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------
+ * Cluster re-sampling: resample_cluster(), PointCloud/mlp_reg.py:172-237 (normal=False): Lloyd
+ * k-means of every frame's cloud seeded with the fitted cluster origins matrices[:, :3, 3]
+ * (sklearn.cluster.k_means(init=..., n_init=1), :204), then every cluster moved into its local
+ * frame with inv(matrices[k]) (:207-213).  SURVEY section 8(f)-2.  float64.
+ *   cloud_xyz/cloud_off  packed frame clouds (F frames);   matrices  F x K x 16
+ *   out_labels (per point), out_centers F x K x 3, out_local_xyz packed like cloud_xyz but each
+ *   frame's points grouped by cluster in cloud order, out_local_off F x (K+1) group offsets
+ *   within the frame, out_n_iter / out_inertia per frame (may be NULL).
+ * ------------------------------------------------------------------------------------- */
+AURDF_API int aurdf_resample_clusters(const double *cloud_xyz, const int32_t *cloud_off,
+                                      const double *matrices, int32_t n_frames, int32_t n_clusters,
+                                      int32_t max_points_per_frame, int32_t max_iter, double tol,
+                                      int32_t *out_labels, double *out_centers, double *out_local_xyz,
+                                      int32_t *out_local_off, int32_t *out_n_iter, double *out_inertia,
+                                      aurdf_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
  * Dual-quaternion library: PointCloud/dq_func.py:4-257 and the four pytorch3d 0.7.7
  * rotation_conversions functions it imports (dq_func.py:2).  n = number of batch elements,
  * dtype F32 or F64, arithmetic in that dtype in the reference's operation order.

@@ -149,3 +149,48 @@ def test_nn_l2_vs_oracle(oracle):
                 continue
             oi, od = oracle.nn_batch(qa[sl].astype(np.float64), ta[toff[g]:toff[g + 1]].astype(np.float64), True)
             assert np.array_equal(idx[sl], oi) and np.array_equal(d2[sl], od)
+
+
+def test_resample_cluster_vs_oracle_and_sklearn():
+    """seeded Lloyd k-means + local frames; labels identical to the oracle (which is
+    pinned against sklearn.cluster.k_means in the CPU tests), local clusters to 1e-12"""
+    import warnings
+    from sklearn.cluster import k_means
+    from autourdf_b200 import synth
+    from autourdf_b200.mlp_reg import resample_cluster
+    from oracle import kmeans_oracle as KO
+    b = synth.make_config("wx200_5", n_seq=1)
+    K = b.n_clusters
+    for f in (0, 3, 8):
+        cloud = b.tgt[b.tgt_off[f]:b.tgt_off[f + 1]]
+        mats = b.init_T[f * K:(f + 1) * K]
+        d = {}
+        got = resample_cluster(cloud, 0, K, mats, _details=d)
+        ref, labels = KO.resample_cluster(cloud, K, mats)
+        assert np.array_equal(d["labels"], labels)
+        assert [g.shape for g in got] == [r.shape for r in ref]
+        for g, r in zip(got, ref):
+            if r.shape[0]:
+                assert np.abs(g - r).max() <= 1e-12
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            c, l, inertia = k_means(cloud, n_clusters=K, init=mats[:, :3, 3], n_init=1)
+        assert np.array_equal(d["labels"], l) and np.abs(d["centers"] - c).max() <= 1e-12
+        assert abs(d["inertia"] - inertia) <= 1e-9 * inertia
+    # a seed far from the cloud -> empty cluster -> re-seeded with the farthest point, like sklearn
+    mats = b.init_T[:K].copy()
+    mats[3, :3, 3] = [5.0, 5.0, 5.0]
+    cloud = b.tgt[b.tgt_off[0]:b.tgt_off[1]]
+    d = {}
+    got = resample_cluster(cloud, 0, K, mats, _details=d)
+    _, labels = KO.resample_cluster(cloud, K, mats)
+    assert np.array_equal(d["labels"], labels)
+
+    class _Seg:                       # the reference passes its Segments object and a frame index
+        class _PC:
+            def __init__(self, p): self.points = p
+        def __init__(self, clouds): self.pc_list = [self._PC(c) for c in clouds]
+    got2 = resample_cluster(_Seg([cloud, cloud]), 1, K, mats)
+    assert all(np.array_equal(a, b_) for a, b_ in zip(got, got2))
+    with pytest.raises(NotImplementedError):
+        resample_cluster(cloud, 0, K, mats, normal=True)
