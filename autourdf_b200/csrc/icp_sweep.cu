@@ -23,13 +23,18 @@
 
 #include <vector>
 
+#include <cooperative_groups.h>
+
 #include "common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace aurdf {
 
 constexpr int kIcpThreads = 256;
 constexpr int kIcpWarps = kIcpThreads / 32;
-constexpr int kQChunk = 512;      // target points staged per shared-memory chunk (12 KB as f64 SoA)
+constexpr int kQChunk = 1024;     // target points staged per shared-memory chunk (24 KB f64 SoA + 16 KB float4)
+constexpr int kClusterCtas = 8;   // CTAs per tile in the cluster variant (large tiles)
 constexpr int kPSmemMax = 2048;   // most source points a tile may keep in shared memory
 
 struct WsLayout {
@@ -596,6 +601,11 @@ __device__ __forceinline__ void warp_sum16(double (&v)[16], int lane) {
 //   warp 1    lane 0: fitness, rmse and open3d's convergence test          -> stop flag
 //   barrier B
 //   warp 3    16 lanes: T <- U T (off the critical path, overlaps the next pass)
+// CS > 1: a thread-block cluster of CS CTAs shares one (large) tile.  Every CTA owns a contiguous
+// slice of the source points and scans all targets; the per-CTA moment sums meet in the leader's
+// shared memory through DSMEM, the leader fits the pose and tests convergence, and the other CTAs
+// read the update back -- two cluster barriers per iteration.
+template <int CS>
 __global__ void __launch_bounds__(kIcpThreads, 2)
 icp_tiles_kernel(const IcpParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -616,13 +626,22 @@ icp_tiles_kernel(const IcpParams p) {
     __shared__ double s_prev[2];              // fitness, rmse of the previous pass
     __shared__ double s_warm[18];             // singular vectors of the previous fit
     __shared__ int s_stop;
+    __shared__ double s_cl[CS][16];           // leader only: per-CTA moment sums of the cluster
+    __shared__ int s_clc[CS];                 // leader only: per-CTA inlier counts
     __shared__ float s_amax[kIcpWarps];       // max |target coordinate - origin| per warp
     __shared__ __align__(8) uint64_t s_bar;
 
     if (p.status_int[0]) return;  // compacted-target capacity exceeded: leave outputs untouched
 
-    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int s0 = p.src_off[b], ns = p.src_off[b + 1] - s0;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int b = blockIdx.x / CS;                       // tile
+    int rank = 0;                                        // CTA within the tile's cluster
+    if constexpr (CS > 1) rank = (int)cg::this_cluster().block_rank();
+    const int ns_tile = p.src_off[b + 1] - p.src_off[b];
+    const int per = (ns_tile + CS - 1) / CS;
+    const int lo = min(ns_tile, rank * per);
+    const int s0 = p.src_off[b] + lo;                    // this CTA's slice of the source points
+    const int ns = min(ns_tile, lo + per) - lo;
     const int nt = p.cnt[b];
     const long long q0 = p.toff[b];
     const bool resident = nt <= kQChunk;
@@ -689,15 +708,22 @@ icp_tiles_kernel(const IcpParams p) {
     const double ox = nt > 0 ? __ldg(p.qx + q0) : 0.0, oy = nt > 0 ? __ldg(p.qy + q0) : 0.0,
                  oz = nt > 0 ? __ldg(p.qz + q0) : 0.0;
 
-    // float32 pre-filter (resident tiles): targets about the origin, rounded to float32, and the
-    // largest coordinate magnitude A_q, which scales the rounding-error bound of the filter
-    const bool use_f32 = resident && nt > 0;
+    // float32 pre-filter: targets about the origin, rounded to float32 (built once for a resident
+    // tile, per staged chunk for a streamed one), and the largest coordinate magnitude A_q, which
+    // scales the rounding-error bound of the filter
+    const bool use_f32 = nt > 0;
     float aq = 0.f;
     if (use_f32) {
         float amax = 0.f;
         for (int j = tid; j < nt; j += kIcpThreads) {
-            const float fx = (float)(sqx[j] - ox), fy = (float)(sqy[j] - oy), fz = (float)(sqz[j] - oz);
-            sqf[j] = make_float4(fx, fy, fz, 0.f);
+            float fx, fy, fz;
+            if (resident) {
+                fx = (float)(sqx[j] - ox); fy = (float)(sqy[j] - oy); fz = (float)(sqz[j] - oz);
+                sqf[j] = make_float4(fx, fy, fz, 0.f);
+            } else {
+                fx = (float)(__ldg(p.qx + q0 + j) - ox); fy = (float)(__ldg(p.qy + q0 + j) - oy);
+                fz = (float)(__ldg(p.qz + q0 + j) - oz);
+            }
             amax = fmaxf(amax, fmaxf(fabsf(fx), fmaxf(fabsf(fy), fabsf(fz))));
         }
 #pragma unroll
@@ -710,7 +736,7 @@ icp_tiles_kernel(const IcpParams p) {
 
     long long dbg_n = 0;
     auto stamp = [&]() {
-        if (p.dbg_clock && b == 0 && tid == 0 && dbg_n < 4096) p.dbg_clock[dbg_n++] = clock64();
+        if (p.dbg_clock && blockIdx.x == 0 && tid == 0 && dbg_n < 4096) p.dbg_clock[dbg_n++] = clock64();
     };
 
     // One correspondence pass.  apply: first move the points by the current update s_U.
@@ -743,17 +769,27 @@ icp_tiles_kernel(const IcpParams p) {
             if (use_f32) {
                 float m1 = INFINITY, m2 = INFINITY;
                 int j1 = -1;
-                float fx = 0.f, fy = 0.f, fz = 0.f;
-                if (active) {
-                    fx = (float)(x - ox); fy = (float)(y - oy); fz = (float)(z - oz);
+                const float fx = (float)(x - ox), fy = (float)(y - oy), fz = (float)(z - oz);
+                for (int c = 0; c < nchunks; ++c) {
+                    const int n = min(kQChunk, nt - c * kQChunk);
+                    const int jbase = c * kQChunk;
+                    if (!resident) {   // stage the chunk and its float32 copy
+                        __syncthreads();
+                        load_chunk(c);
+                        for (int j = tid; j < n; j += kIcpThreads)
+                            sqf[j] = make_float4((float)(sqx[j] - ox), (float)(sqy[j] - oy), (float)(sqz[j] - oz), 0.f);
+                        __syncthreads();
+                    }
+                    if (active) {
 #pragma unroll 4
-                    for (int j = sub; j < nt; j += S) {
-                        const float4 q = sqf[j];
-                        const float dx = fx - q.x, dy = fy - q.y, dz = fz - q.z;
-                        const float d = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-                        m2 = fminf(m2, fmaxf(m1, d));
-                        j1 = d < m1 ? j : j1;
-                        m1 = fminf(m1, d);
+                        for (int j = sub; j < n; j += S) {
+                            const float4 q = sqf[j];
+                            const float dx = fx - q.x, dy = fy - q.y, dz = fz - q.z;
+                            const float d = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+                            m2 = fminf(m2, fmaxf(m1, d));
+                            j1 = d < m1 ? jbase + j : j1;
+                            m1 = fminf(m1, d);
+                        }
                     }
                 }
                 for (int o = S >> 1; o > 0; o >>= 1) {
@@ -773,15 +809,19 @@ icp_tiles_kernel(const IcpParams p) {
                     if (nt == 1 || (m2 - m1 > 2.f * tau && m2 < INFINITY)) {
                         need_exact = false;
                         if (sub == 0) {
-                            const double dx = __dsub_rn(x, sqx[j1]), dy = __dsub_rn(y, sqy[j1]), dz = __dsub_rn(z, sqz[j1]);
+                            double qx_, qy_, qz_;
+                            if (resident) { qx_ = sqx[j1]; qy_ = sqy[j1]; qz_ = sqz[j1]; }
+                            else { qx_ = __ldg(p.qx + q0 + j1); qy_ = __ldg(p.qy + q0 + j1); qz_ = __ldg(p.qz + q0 + j1); }
+                            const double dx = __dsub_rn(x, qx_), dy = __dsub_rn(y, qy_), dz = __dsub_rn(z, qz_);
                             bd = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
                             bj = j1;
                         }
                     }
                 }
             }
-            // (streamed tiles always walk the chunks: the loop holds block barriers)
-            const bool warp_scans = !resident || __any_sync(0xffffffffu, need_exact);
+            // exact rescan: per warp for a resident tile; block-wide vote for a streamed one, whose
+            // chunk loop holds block barriers
+            const bool warp_scans = resident ? (bool)__any_sync(0xffffffffu, need_exact) : (bool)__syncthreads_or(need_exact);
             for (int c = 0; warp_scans && c < nchunks; ++c) {
                 if (!resident) {
                     __syncthreads();  // everyone done with the previous chunk
@@ -858,6 +898,46 @@ icp_tiles_kernel(const IcpParams p) {
         __syncwarp();
         return c;
     };
+    // cluster variant: totals over all CTAs of the tile, from the slots the CTAs filled in the leader
+    auto cluster_totals = [&](int w) -> int {
+        if (lane < 16) {
+            double t = s_cl[0][lane];
+#pragma unroll
+            for (int r = 1; r < CS; ++r) t += s_cl[r][lane];
+            s_tot[w][lane] = t;
+        }
+        int c = 0;
+#pragma unroll
+        for (int r = 0; r < CS; ++r) c += s_clc[r];
+        __syncwarp();
+        return c;
+    };
+    // every CTA: publish its totals to the leader, then the two cluster barriers around the fit
+    auto cluster_publish = [&]() {
+        if constexpr (CS > 1) {
+            cg::cluster_group cluster = cg::this_cluster();
+            if (warp == 0) {
+                const int c = totals(0);
+                double *dst = cluster.map_shared_rank(&s_cl[0][0], 0);
+                int *dstc = cluster.map_shared_rank(&s_clc[0], 0);
+                if (lane < 16) dst[rank * 16 + lane] = s_tot[0][lane];
+                if (lane == 16) dstc[rank] = c;
+            }
+            cluster.sync();
+        }
+    };
+    auto cluster_fetch = [&]() {
+        if constexpr (CS > 1) {
+            cg::cluster_group cluster = cg::this_cluster();
+            cluster.sync();
+            if (rank != 0) {
+                const double *srcU = cluster.map_shared_rank(&s_U[0], 0);
+                const int *srcS = cluster.map_shared_rank(&s_stop, 0);
+                if (tid < 12) s_U[tid] = srcU[tid];
+                if (tid == 12) s_stop = *srcS;
+            }
+        }
+    };
 
     // Kabsch / umeyama update from the totals of consumer slot 0 (lane 0 of warp 0)
     bool have_warm = false;
@@ -906,42 +986,49 @@ icp_tiles_kernel(const IcpParams p) {
     stamp();
     pass(false);
     __syncthreads();  // barrier A
-    if (warp == 0) {
-        const int c = totals(0);
-        if (lane == 0 && p.max_iter > 0) fit_pose(c);
-    } else if (warp == 1) {
-        const int c = totals(1);
-        if (lane == 0) {
-            s_prev[0] = c > 0 ? (double)c / (double)ns : 0.0;
-            s_prev[1] = c > 0 ? sqrt(s_tot[1][0] / (double)c) : 0.0;
+    cluster_publish();
+    if (rank == 0) {
+        if (warp == 0) {
+            const int c = CS > 1 ? cluster_totals(0) : totals(0);
+            if (lane == 0 && p.max_iter > 0) fit_pose(c);
+        } else if (warp == 1) {
+            const int c = CS > 1 ? cluster_totals(1) : totals(1);
+            if (lane == 0) {
+                s_prev[0] = c > 0 ? (double)c / (double)ns_tile : 0.0;
+                s_prev[1] = c > 0 ? sqrt(s_tot[1][0] / (double)c) : 0.0;
+            }
         }
     }
+    cluster_fetch();
     __syncthreads();  // barrier B
 
     int iters = 0;
     for (int it = 0; it < p.max_iter; ++it) {
-        stamp();  // [4k+0] iteration start
-        if (warp == kIcpWarps - 1) compose_pose();  // uses s_U of this iteration; next write is after barrier A
+        stamp();  // [7k+0] iteration start
+        if (rank == 0 && warp == kIcpWarps - 1) compose_pose();  // uses s_U of this iteration; next write is after barrier A
         pass(true);
-        stamp();  // [4k+1] pass done (warp 0)
+        stamp();  // [+4] pass done (warp 0)
         __syncthreads();  // barrier A
-        stamp();  // [4k+2] barrier A passed
-        if (warp == 0) {
-            // speculative: the fit for iteration it+1 runs while warp 1 decides whether to stop
-            const int c = totals(0);
-            if (lane == 0 && it + 1 < p.max_iter) fit_pose(c);
-        }
-        else if (warp == 1) {
-            const int c = totals(1);
-            if (lane == 0) {
-                const double fit = c > 0 ? (double)c / (double)ns : 0.0;
-                const double rmse = c > 0 ? sqrt(s_tot[1][0] / (double)c) : 0.0;
-                s_stop = (fabs(s_prev[0] - fit) < p.rel_fit && fabs(s_prev[1] - rmse) < p.rel_rmse) ? 1 : 0;
-                s_prev[0] = fit;
-                s_prev[1] = rmse;
+        stamp();  // [+5] barrier A passed
+        cluster_publish();
+        if (rank == 0) {
+            if (warp == 0) {
+                // speculative: the fit for iteration it+1 runs while warp 1 decides whether to stop
+                const int c = CS > 1 ? cluster_totals(0) : totals(0);
+                if (lane == 0 && it + 1 < p.max_iter) fit_pose(c);
+            } else if (warp == 1) {
+                const int c = CS > 1 ? cluster_totals(1) : totals(1);
+                if (lane == 0) {
+                    const double fit = c > 0 ? (double)c / (double)ns_tile : 0.0;
+                    const double rmse = c > 0 ? sqrt(s_tot[1][0] / (double)c) : 0.0;
+                    s_stop = (fabs(s_prev[0] - fit) < p.rel_fit && fabs(s_prev[1] - rmse) < p.rel_rmse) ? 1 : 0;
+                    s_prev[0] = fit;
+                    s_prev[1] = rmse;
+                }
             }
         }
-        stamp();  // [4k+3] fit done
+        stamp();  // [+6] fit done
+        cluster_fetch();
         __syncthreads();  // barrier B
         iters = it + 1;
         if (s_stop) break;
@@ -949,7 +1036,7 @@ icp_tiles_kernel(const IcpParams p) {
     __syncthreads();
 
     // outputs: pose (cluster_icp.py:161-165), world cluster = T * S (:167), correspondences
-    if (tid == 0) {
+    if (rank == 0 && tid == 0) {
         if (p.ori_only) {
             s_T[3] = p.init_T[16 * (size_t)b + 3];
             s_T[7] = p.init_T[16 * (size_t)b + 7];
@@ -961,7 +1048,14 @@ icp_tiles_kernel(const IcpParams p) {
         p.out_ntgt[b] = nt;
     }
     __syncthreads();
-    if (tid < 16) p.out_T[16 * (size_t)b + tid] = s_T[tid];
+    if constexpr (CS > 1) {   // every CTA of the cluster needs the leader's final pose
+        cg::cluster_group cluster = cg::this_cluster();
+        cluster.sync();
+        if (rank != 0 && tid < 16) s_T[tid] = cluster.map_shared_rank(&s_T[0], 0)[tid];
+        cluster.sync();       // the leader's shared memory must outlive the reads
+        __syncthreads();
+    }
+    if (rank == 0 && tid < 16) p.out_T[16 * (size_t)b + tid] = s_T[tid];
     const bool aff = s_T[12] == 0.0 && s_T[13] == 0.0 && s_T[14] == 0.0 && s_T[15] == 1.0;
     for (int i = tid; i < ns; i += kIcpThreads) {
         const size_t e = 3 * (size_t)(s0 + i);
@@ -1058,15 +1152,22 @@ extern "C" int aurdf_icp_sweep(const void *src_xyz, int pts_dtype, const int32_t
     int *qi = (int *)(ws + L.qi);
     double *pspill = (double *)(ws + L.pspill);
 
-    // source points live in shared memory up to p_cap per tile (bounded by the caller's hint and
-    // kPSmemMax); larger tiles keep them in the workspace spill area (sized by total_src_points)
+    // Large tiles (caller's hint) run as clusters of kClusterCtas CTAs, each owning a slice of the
+    // source points.  Source points live in shared memory up to p_cap per CTA (bounded by the hint and
+    // kPSmemMax); larger slices keep them in the workspace spill area (sized by total_src_points).
+    const bool use_cluster = max_src_per_tile > 384;
     int p_cap = max_src_per_tile > 0 ? max_src_per_tile : 256;
+    if (use_cluster) p_cap = (p_cap + kClusterCtas - 1) / kClusterCtas;
     if (p_cap > kPSmemMax) p_cap = kPSmemMax;
     p_cap = (p_cap + 1) & ~1;
     const size_t smem = (size_t)3 * kQChunk * sizeof(double) + (size_t)kQChunk * sizeof(float4) +
                         (size_t)3 * p_cap * sizeof(double) + (size_t)p_cap * sizeof(int);
-    if (smem > 48 * 1024)
-        AURDF_CUDA_CHECK(cudaFuncSetAttribute(icp_tiles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (smem > 32 * 1024) {   // static + dynamic beyond the default 48 KiB needs the opt-in
+        if (use_cluster)
+            AURDF_CUDA_CHECK(cudaFuncSetAttribute(icp_tiles_kernel<kClusterCtas>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        else
+            AURDF_CUDA_CHECK(cudaFuncSetAttribute(icp_tiles_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
 
     box_count_kernel<<<n_tiles, kIcpThreads, 0, stream>>>(box_xyz, box_dtype, box_off, tgt_xyz, pts_dtype, tgt_off,
                                                           tile_frame, box_scale, box, cnt);
@@ -1088,7 +1189,23 @@ extern "C" int aurdf_icp_sweep(const void *src_xyz, int pts_dtype, const int32_t
         AURDF_CUDA_CHECK(cudaEventCreate(&ev.b));
         AURDF_CUDA_CHECK(cudaEventRecord(ev.a, stream));
     }
-    icp_tiles_kernel<<<n_tiles, kIcpThreads, smem, stream>>>(P);
+    if (use_cluster) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)n_tiles * kClusterCtas);
+        cfg.blockDim = dim3(kIcpThreads);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = kClusterCtas;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        AURDF_CUDA_CHECK(cudaLaunchKernelEx(&cfg, icp_tiles_kernel<kClusterCtas>, P));
+    } else {
+        icp_tiles_kernel<1><<<n_tiles, kIcpThreads, smem, stream>>>(P);
+    }
     if (g_prof_on) {
         AURDF_CUDA_CHECK(cudaEventRecord(ev.b, stream));
         g_prof.push_back(ev);
