@@ -1,0 +1,429 @@
+// icp_small.cu -- the per-tile ICP of icp_sweep.cu, re-cut for the tiles of the named configs
+// (n_s <= 320 source points, n_t <= 768 masked targets: wx200 / franka / allegro_hand).
+//
+// Why a second kernel.  One launch of the sweep is bounded by the iteration latency of its slowest
+// tile (68 ICP iterations against a mean of 14 on wx200_5), not by issue or memory throughput, and
+// that tile used to start only in the third wave of CTAs.  This kernel therefore
+//   * keeps a tile's whole state in < 30 KB of shared memory and <= 72 registers, so 7 CTAs of
+//     128 threads are resident per SM: all 900 tiles of wx200_5 start at t = 0;
+//   * scans targets two at a time with packed float32 arithmetic (add/mul/fma.f32x2) and tracks
+//     best / second-best as one 32-bit key per target (distance bits | index), 5 integer
+//     min/max per pair instead of compare+select chains;
+//   * replaces the per-lane 16-accumulator moment sums and the transposing shuffle reduction by a
+//     shared-memory reduction with one thread group per moment;
+//   * fits the pose with the shortened Newton-on-SO(3) iteration (kabsch_rotation_newton3).
+// Semantics are those of icp_tiles_kernel (open3d RegistrationICP point-to-point inside
+// masked_icp, cluster_icp.py:118-191): the argmin is certified against float64 or re-done in
+// float64 with the reference's operation order, so correspondences stay bit-identical.
+#include <math.h>
+
+#include "icp_common.cuh"
+
+namespace aurdf {
+
+constexpr uint32_t kIdxMask = 0x3FFu;   // low mantissa bits of a key hold the target index (< 1024)
+static_assert(kSmNt32 <= 1024 && kSmNt32 % 2 == 0, "index field");
+
+constexpr size_t kSmallSmemBytes = (size_t)(kSmNt32 / 2) * (sizeof(float4) + sizeof(float2)) +
+                                   (size_t)3 * kSmNt64 * sizeof(double) + (size_t)3 * kSmNs * sizeof(double) +
+                                   (size_t)kSmNs * sizeof(double) + (size_t)kSmNs * sizeof(int);
+
+template <int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB)
+icp_small_kernel(const IcpParams p) {
+    constexpr int kWarps = NT / 32;
+    constexpr int G = NT / 16;   // lanes per moment in the reduction (8 or 16: inside one warp)
+    static_assert(kWarps >= 4 && G <= 32, "thread count");
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float4 *sxy = reinterpret_cast<float4 *>(smem_raw);             // (-x0, -x1, -y0, -y1) of a target pair
+    float2 *sz = reinterpret_cast<float2 *>(sxy + kSmNt32 / 2);     // (-z0, -z1)
+    double *sqx = reinterpret_cast<double *>(sz + kSmNt32 / 2);     // float64 targets (n_t <= kSmNt64)
+    double *sqy = sqx + kSmNt64;
+    double *sqz = sqy + kSmNt64;
+    double *spx = sqz + kSmNt64;                                    // current source points
+    double *spy = spx + kSmNs;
+    double *spz = spy + kSmNs;
+    double *sbd = spz + kSmNs;                                      // exact squared distance to the match
+    int *scj = reinterpret_cast<int *>(sbd + kSmNs);                // match (compacted index) or -1
+
+    __shared__ double s_tot[16];   // moment totals of the current pass
+    __shared__ int s_cnt;          // inlier count of the current pass
+    __shared__ double s_U[16];     // current update (row-major 4x4)
+    __shared__ double s_T[16];     // accumulated pose
+    __shared__ double s_prev[2];   // fitness, rmse of the previous pass
+    __shared__ double s_warm[18];  // singular vectors of the previous Jacobi fit (fallback only)
+    __shared__ int s_stop;
+    __shared__ float s_amax[kWarps];
+    __shared__ __align__(8) uint64_t s_bar;
+
+    if (p.status_int[0]) return;   // compacted-target capacity exceeded: leave outputs untouched
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int b = blockIdx.x;
+    const int s0 = p.src_off[b];
+    const int ns = p.src_off[b + 1] - s0;
+    const int nt = p.cnt[b];
+    if (!tile_is_small(ns, nt)) return;   // the general kernel owns this tile
+    const long long q0 = p.toff[b];
+    const double *gqx = p.qx + q0, *gqy = p.qy + q0, *gqz = p.qz + q0;
+    const bool q64s = nt <= kSmNt64;      // float64 targets fit in shared memory
+    const double *qxp = q64s ? sqx : gqx, *qyp = q64s ? sqy : gqy, *qzp = q64s ? sqz : gqz;
+
+    if (tid == 0) {
+        mbar_init(&s_bar, 1);
+        mbar_fence_init();
+        s_stop = 0;
+    }
+    if (tid < 16) {
+        s_T[tid] = p.init_T[16 * (size_t)b + tid];
+        s_U[tid] = (tid % 5 == 0) ? 1.0 : 0.0;
+    }
+    __syncthreads();
+
+    // float64 targets: three bulk copies (TMA engine) on one mbarrier
+    if (q64s && nt > 0) {
+        const uint32_t bytes = (uint32_t)(((nt + 1) & ~1) * sizeof(double));
+        if (tid == 0) {
+            fence_proxy_async();
+            mbar_arrive_expect_tx(&s_bar, 3 * bytes);
+            bulk_g2s(sqx, gqx, bytes, &s_bar);
+            bulk_g2s(sqy, gqy, bytes, &s_bar);
+            bulk_g2s(sqz, gqz, bytes, &s_bar);
+        }
+    }
+
+    // P <- T0 * S (overlaps the bulk copies)
+    {
+        const bool aff0 = s_T[12] == 0.0 && s_T[13] == 0.0 && s_T[14] == 0.0 && s_T[15] == 1.0;
+        for (int i = tid; i < ns; i += NT) {
+            const size_t e = 3 * (size_t)(s0 + i);
+            double x = ld_coord(p.src, p.pts_dtype, e), y = ld_coord(p.src, p.pts_dtype, e + 1),
+                   z = ld_coord(p.src, p.pts_dtype, e + 2);
+            transform_point(s_T, aff0, x, y, z);
+            spx[i] = x; spy[i] = y; spz[i] = z;
+        }
+    }
+    if (q64s && nt > 0) mbar_wait(&s_bar, 0);
+
+    // moments are accumulated about the tile's first target point (kills cancellation); the
+    // float32 filter works in the same frame
+    const double ox = nt > 0 ? qxp[0] : 0.0, oy = nt > 0 ? qyp[0] : 0.0, oz = nt > 0 ? qzp[0] : 0.0;
+
+    // float32 copies of the targets, negated (the scan adds), two per entry; an odd tail is padded
+    // with a point no source can match.  aq = largest coordinate magnitude, scales the error bound.
+    const int npairs = (nt + 1) >> 1;
+    float aq = 0.f;
+    {
+        float amax = 0.f;
+        for (int jj = tid; jj < npairs; jj += NT) {
+            const int j0 = 2 * jj, j1 = j0 + 1;
+            const float ax = (float)(qxp[j0] - ox), ay = (float)(qyp[j0] - oy), az = (float)(qzp[j0] - oz);
+            float bx = 1e18f, by = 0.f, bz = 0.f;
+            amax = fmaxf(amax, fmaxf(fabsf(ax), fmaxf(fabsf(ay), fabsf(az))));
+            if (j1 < nt) {
+                bx = (float)(qxp[j1] - ox); by = (float)(qyp[j1] - oy); bz = (float)(qzp[j1] - oz);
+                amax = fmaxf(amax, fmaxf(fabsf(bx), fmaxf(fabsf(by), fabsf(bz))));
+            }
+            sxy[jj] = make_float4(-ax, -bx, -ay, -by);
+            sz[jj] = make_float2(-az, -bz);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+        if (lane == 0) s_amax[warp] = amax;
+        __syncthreads();
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) aq = fmaxf(aq, s_amax[w]);
+    }
+
+    // split factor: S lanes share one source point when the tile is narrower than the CTA
+    int S = 1;
+    while (S < 32 && ns * (S * 2) <= NT) S *= 2;
+    const int pts_per_round = NT / S;
+    const int rounds = (ns + pts_per_round - 1) / pts_per_round;
+    const int sub = tid & (S - 1);
+
+    long long dbg_n = 0;
+    auto stamp = [&]() {
+        if (p.dbg_clock && blockIdx.x == 0 && tid == 0 && dbg_n < 4096) p.dbg_clock[dbg_n++] = clock64();
+    };
+
+    // ---- phase A: move the points by the current update, find every point's nearest target ----
+    auto pass = [&](bool apply) {
+        for (int r = 0; r < rounds; ++r) {
+            const int i = tid / S + r * pts_per_round;
+            const bool active = i < ns;
+            double x = 0, y = 0, z = 0;
+            if (active) {
+                x = spx[i]; y = spy[i]; z = spz[i];
+                if (apply) transform_point(s_U, true, x, y, z);
+            }
+            if (apply) {
+                if (S > 1) __syncwarp();   // the S lanes of a point have all read the old value
+                if (active && sub == 0) { spx[i] = x; spy[i] = y; spz[i] = z; }
+            }
+            if (apply && r == 0) stamp();   // [+1] P update done
+            double bd = INFINITY;
+            int bj = -1;
+            bool need_exact = active && nt > 0;
+            if (nt > 0) {
+                // float32 pre-filter.  key = (bits of the float32 squared distance, low 10 bits replaced
+                // by the target index): unsigned order = distance order up to 2^-13 relative, ties and
+                // near-ties fall to the exact scan below through the certificate.
+                const float fx = (float)(x - ox), fy = (float)(y - oy), fz = (float)(z - oz);
+                uint32_t m1 = 0xFFFFFFFFu, m2 = 0xFFFFFFFFu;
+                if (active) {
+                    const float2 fx2 = make_float2(fx, fx), fy2 = make_float2(fy, fy), fz2 = make_float2(fz, fz);
+                    uint32_t idx = 2u * (uint32_t)sub;
+                    const uint32_t step = 2u * (uint32_t)S;
+#pragma unroll 4
+                    for (int jj = sub; jj < npairs; jj += S, idx += step) {
+                        const float4 qxy = sxy[jj];
+                        const float2 qz = sz[jj];
+                        const float2 dx = __fadd2_rn(fx2, make_float2(qxy.x, qxy.y));
+                        const float2 dy = __fadd2_rn(fy2, make_float2(qxy.z, qxy.w));
+                        const float2 dz = __fadd2_rn(fz2, qz);
+                        float2 d = __fmul2_rn(dx, dx);
+                        d = __ffma2_rn(dy, dy, d);
+                        d = __ffma2_rn(dz, dz, d);
+                        const uint32_t k0 = (__float_as_uint(d.x) & ~kIdxMask) | idx;
+                        const uint32_t k1 = (__float_as_uint(d.y) & ~kIdxMask) | (idx + 1u);
+                        const uint32_t lo = min(k0, k1), hi = max(k0, k1);
+                        m2 = __vimin3_u32(m2, hi, max(m1, lo));
+                        m1 = min(m1, lo);
+                    }
+                }
+                for (int o = S >> 1; o > 0; o >>= 1) {
+                    const uint32_t om1 = __shfl_xor_sync(0xffffffffu, m1, o), om2 = __shfl_xor_sync(0xffffffffu, m2, o);
+                    m2 = __vimin3_u32(m2, om2, max(m1, om1));
+                    m1 = min(m1, om1);
+                }
+                const int j1 = (int)(m1 & kIdxMask);
+                if (active && m1 != 0xFFFFFFFFu && j1 < nt) {
+                    // true float32 distances: best <= m1hi, every other target >= m2lo.  The float32
+                    // distance itself is within tau/16 of the real one (see icp_sweep.cu), tau taken at
+                    // the larger value.
+                    const float m1hi = __uint_as_float(m1 | kIdxMask);
+                    const float m2lo = __uint_as_float(m2 & ~kIdxMask), m2hi = __uint_as_float(m2 | kIdxMask);
+                    const float u = 5.9604645e-8f;
+                    const float amag = fmaxf(aq, fmaxf(fabsf(fx), fmaxf(fabsf(fy), fabsf(fz))));
+                    const float dl = 4.f * u * amag;
+                    const float tau = 16.f * (dl * sqrtf(m2hi) * 1.001f + dl * dl + u * m2hi);
+                    if (nt == 1 || (m2lo - m1hi > 2.f * tau && m2hi < INFINITY)) {
+                        need_exact = false;
+                        if (sub == 0) {
+                            const double dx = __dsub_rn(x, qxp[j1]), dy = __dsub_rn(y, qyp[j1]), dz = __dsub_rn(z, qzp[j1]);
+                            bd = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+                            bj = j1;
+                        }
+                    }
+                }
+            }
+            // exact rescan of the uncertified points of this warp (~1e-3 of them; duplicates always):
+            // float64, the reference's operation order, strict '<' in ascending index order
+            if (__any_sync(0xffffffffu, need_exact)) {
+                if (need_exact) {
+                    for (int j = sub; j < nt; j += S) {
+                        const double dx = __dsub_rn(x, qxp[j]), dy = __dsub_rn(y, qyp[j]), dz = __dsub_rn(z, qzp[j]);
+                        const double d = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+                        if (d < bd) { bd = d; bj = j; }
+                    }
+                }
+                for (int o = S >> 1; o > 0; o >>= 1) {   // (d, j) lexicographic min across the S lanes
+                    const double od = __shfl_xor_sync(0xffffffffu, bd, o);
+                    const int oj = __shfl_xor_sync(0xffffffffu, bj, o);
+                    if (oj >= 0 && (od < bd || (od == bd && oj < bj) || bj < 0)) { bd = od; bj = oj; }
+                }
+            }
+            if (active && sub == 0) {
+                const bool inl = bj >= 0 && bd < p.r2;
+                scj[i] = inl ? bj : -1;
+                sbd[i] = bd;
+            }
+        }
+    };
+
+    // ---- phase B: the 16 moment sums + inlier count, one group of G lanes per moment ----
+    //   0: sum d^2   1-3: sum a   4-6: sum b   7-15: sum b_r a_c     (a = source, b = matched target,
+    //   both about the origin o)
+    auto reduce = [&]() {
+        const int m = tid / G, g = tid % G;
+        const double *pa = nullptr, *pq = nullptr;
+        double oa = 0.0, oq = 0.0;
+        if (m >= 1 && m <= 3) {
+            pa = m == 1 ? spx : (m == 2 ? spy : spz);
+            oa = m == 1 ? ox : (m == 2 ? oy : oz);
+        } else if (m >= 4) {
+            const int rr = m <= 6 ? m - 4 : (m - 7) / 3;
+            pq = rr == 0 ? qxp : (rr == 1 ? qyp : qzp);
+            oq = rr == 0 ? ox : (rr == 1 ? oy : oz);
+            if (m >= 7) {
+                const int cc = (m - 7) % 3;
+                pa = cc == 0 ? spx : (cc == 1 ? spy : spz);
+                oa = cc == 0 ? ox : (cc == 1 ? oy : oz);
+            }
+        }
+        double acc = 0.0;
+        int cnt = 0;
+        for (int i = g; i < ns; i += G) {
+            const int j = scj[i];
+            if (j >= 0) {
+                if (m == 0) {
+                    acc += sbd[i];
+                    ++cnt;
+                } else {
+                    const double a = pa ? pa[i] - oa : 1.0;
+                    const double bq = pq ? pq[j] - oq : 1.0;
+                    acc += a * bq;
+                }
+            }
+        }
+#pragma unroll
+        for (int o = G >> 1; o > 0; o >>= 1) {
+            acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        }
+        if (g == 0) {
+            s_tot[m] = acc;
+            if (m == 0) s_cnt = cnt;
+        }
+    };
+
+    // Kabsch / umeyama update from the totals (one lane)
+    bool have_warm = false;
+    auto fit_pose = [&]() {
+        const double *t = s_tot;
+        const int c = s_cnt;
+        double Um[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
+        if (c > 0) {
+            const double inv = rcp_nr2((double)c);
+            const double ma[3] = {t[1] * inv, t[2] * inv, t[3] * inv};
+            const double mb[3] = {t[4] * inv, t[5] * inv, t[6] * inv};
+            double sigma[3][3], R[3][3];
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+#pragma unroll
+                for (int cc = 0; cc < 3; ++cc) sigma[r][cc] = t[7 + 3 * r + cc] * inv - mb[r] * ma[cc];
+            if (!kabsch_rotation_newton3(sigma, R)) {
+                kabsch_rotation(sigma, R, s_warm, have_warm);   // reflection / rank-deficient / large step
+                have_warm = true;
+            }
+            const double mua[3] = {ma[0] + ox, ma[1] + oy, ma[2] + oz};
+            const double mub[3] = {mb[0] + ox, mb[1] + oy, mb[2] + oz};
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                Um[4 * r + 0] = R[r][0]; Um[4 * r + 1] = R[r][1]; Um[4 * r + 2] = R[r][2];
+                Um[4 * r + 3] = mub[r] - (R[r][0] * mua[0] + R[r][1] * mua[1] + R[r][2] * mua[2]);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 12; ++k) s_U[k] = Um[k];
+    };
+
+    // T <- U * T, one lane per entry, entries summed left to right with each operation rounded
+    auto compose_pose = [&]() {
+        double v = 0.0;
+        if (lane < 16) {
+            const int r = lane >> 2, cc = lane & 3;
+            v = __dmul_rn(s_U[4 * r], s_T[cc]);
+            v = __dadd_rn(v, __dmul_rn(s_U[4 * r + 1], s_T[4 + cc]));
+            v = __dadd_rn(v, __dmul_rn(s_U[4 * r + 2], s_T[8 + cc]));
+            v = __dadd_rn(v, __dmul_rn(s_U[4 * r + 3], s_T[12 + cc]));
+        }
+        __syncwarp();
+        if (lane < 16) s_T[lane] = v;
+    };
+
+    stamp();
+    pass(false);
+    __syncthreads();
+    reduce();
+    __syncthreads();
+    if (warp == 0) {
+        if (lane == 0 && p.max_iter > 0) fit_pose();
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const int c = s_cnt;
+            s_prev[0] = c > 0 ? (double)c / (double)ns : 0.0;
+            s_prev[1] = c > 0 ? sqrt(s_tot[0] / (double)c) : 0.0;
+        }
+    }
+    __syncthreads();
+
+    int iters = 0;
+    for (int it = 0; it < p.max_iter; ++it) {
+        stamp();   // [7k+0] iteration start
+        if (warp == kWarps - 1) compose_pose();   // uses s_U of this iteration; its next write is after barrier 2
+        pass(true);
+        stamp();   // [+2] NN done
+        __syncthreads();   // barrier 1: matches and moved points visible
+        stamp();   // [+3]
+        reduce();
+        stamp();   // [+4] moment sums done
+        __syncthreads();   // barrier 2: totals visible
+        stamp();   // [+5]
+        if (warp == 0) {
+            // speculative: the fit for iteration it+1 runs while warp 1 decides whether to stop
+            if (lane == 0 && it + 1 < p.max_iter) fit_pose();
+        } else if (warp == 1) {
+            if (lane == 0) {
+                const int c = s_cnt;
+                const double fit = c > 0 ? (double)c / (double)ns : 0.0;
+                const double rmse = c > 0 ? sqrt(s_tot[0] / (double)c) : 0.0;
+                s_stop = (fabs(s_prev[0] - fit) < p.rel_fit && fabs(s_prev[1] - rmse) < p.rel_rmse) ? 1 : 0;
+                s_prev[0] = fit;
+                s_prev[1] = rmse;
+            }
+        }
+        stamp();   // [+6] fit done
+        __syncthreads();   // barrier 3: update and stop flag visible
+        iters = it + 1;
+        if (s_stop) break;
+    }
+    __syncthreads();
+
+    // outputs: pose (cluster_icp.py:161-165), world cluster = T * S (:167), correspondences
+    if (tid == 0) {
+        if (p.ori_only) {
+            s_T[3] = p.init_T[16 * (size_t)b + 3];
+            s_T[7] = p.init_T[16 * (size_t)b + 7];
+            s_T[11] = p.init_T[16 * (size_t)b + 11];
+        }
+        p.out_fit[b] = s_prev[0];
+        p.out_rmse[b] = s_prev[1];
+        p.out_iters[b] = iters;
+        p.out_ntgt[b] = nt;
+    }
+    __syncthreads();
+    if (tid < 16) p.out_T[16 * (size_t)b + tid] = s_T[tid];
+    const bool aff = s_T[12] == 0.0 && s_T[13] == 0.0 && s_T[14] == 0.0 && s_T[15] == 1.0;
+    for (int i = tid; i < ns; i += NT) {
+        const size_t e = 3 * (size_t)(s0 + i);
+        double x = ld_coord(p.src, p.pts_dtype, e), y = ld_coord(p.src, p.pts_dtype, e + 1),
+               z = ld_coord(p.src, p.pts_dtype, e + 2);
+        transform_point(s_T, aff, x, y, z);
+        p.out_world[e] = x; p.out_world[e + 1] = y; p.out_world[e + 2] = z;
+        const int j = scj[i];
+        p.out_corr[s0 + i] = j >= 0 ? __ldg(p.qi + q0 + j) : -1;
+    }
+}
+
+// host side: launch over all tiles (CTAs of other classes exit at once)
+int launch_icp_small(const IcpParams &P, int n_tiles, int variant, cudaStream_t stream) {
+    static bool configured[64] = {};
+    int dev = 0;
+    AURDF_CUDA_CHECK(cudaGetDevice(&dev));
+    if (dev >= 0 && dev < 64 && !configured[dev]) {
+        // 7 x (29.3 KB + static) per SM only fits with the carve-out at its maximum
+        AURDF_CUDA_CHECK(cudaFuncSetAttribute(icp_small_kernel<128, 7>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        AURDF_CUDA_CHECK(cudaFuncSetAttribute(icp_small_kernel<256, 4>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        configured[dev] = true;
+    }
+    if (variant == 256)
+        icp_small_kernel<256, 4><<<n_tiles, 256, kSmallSmemBytes, stream>>>(P);
+    else
+        icp_small_kernel<128, 7><<<n_tiles, 128, kSmallSmemBytes, stream>>>(P);
+    return AURDF_OK;
+}
+
+}  // namespace aurdf

@@ -20,12 +20,13 @@
 // float64 CPU reference (no FMA contraction), otherwise near-tie correspondences flip.
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include <vector>
 
 #include <cooperative_groups.h>
 
-#include "common.cuh"
+#include "icp_common.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -269,313 +270,8 @@ mask_fill_kernel(const void *__restrict__ tgt_xyz, int pts_dtype, const int *__r
 }
 
 // ------------------------------------------------------------------------------------------
-// 3x3 SVD by two-sided Jacobi (Eigen JacobiSVD semantics): A = U diag(S) V^T,
-// S sorted descending and non-negative.  Static indices keep everything in registers.
-// This is the serial section of every ICP iteration (one lane), so it is written for latency:
-// three reciprocal square roots per rotation and no division or square root.
-// ------------------------------------------------------------------------------------------
-
-// 1/sqrt(x) to ~1 ulp: MUFU.RSQ64H seed (rsqrt.approx.f64, ~20 bits) + two Newton steps.
-__device__ __forceinline__ double fast_rsqrt(double x) {
-    if (!(x > 1e-290 && x < 1e290)) return rsqrt(x);  // subnormal / huge / NaN: library path
-    double y;
-    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-    const double hx = 0.5 * x;
-    y = y * (1.5 - hx * y * y);
-    y = y * (1.5 - hx * y * y);
-    return y;
-}
-
-template <int P, int Q>
-__device__ __forceinline__ void jacobi_pair(double (&W)[3][3], double (&U)[3][3], double (&V)[3][3],
-                                            double &maxdiag, bool &finished) {
-    const double tiny = 2.2250738585072014e-308;
-    const double thr = fmax(tiny, 4.440892098500626e-16 * maxdiag);
-    if (!(fabs(W[P][Q]) > thr || fabs(W[Q][P]) > thr)) return;
-    finished = false;
-    // 2x2 block on (Q,P), Q < P
-    const double m00 = W[Q][Q], m01 = W[Q][P], m10 = W[P][Q], m11 = W[P][P];
-    // step 1: rotation R1 = [c1 s1; -s1 c1] that makes the block symmetric: (c1,s1) = (t,d)/|(t,d)|
-    const double t = m00 + m11, d = m10 - m01;
-    double c1 = 1.0, s1 = 0.0;
-    const double n1 = t * t + d * d;
-    if (fabs(d) >= tiny && n1 > 1e-290) {
-        const double r = fast_rsqrt(n1);
-        c1 = t * r;
-        s1 = d * r;
-    }
-    const double a00 = c1 * m00 + s1 * m10, a01 = c1 * m01 + s1 * m11, a11 = -s1 * m01 + c1 * m11;
-    // step 2: symmetric Jacobi J = [c2 s2; -s2 c2] with tan = t2 the small root of
-    // t^2 - 2 tau t - 1 = 0, tau = h / (2 a01), h = a00 - a11:
-    //   (c2, s2) = (|h| + w, -sgn(h) 2 a01) / norm,  w = sqrt(h^2 + 4 a01^2)
-    double c2 = 1.0, s2 = 0.0;
-    if (fabs(a01) >= tiny) {
-        const double h = a00 - a11, b2 = 2.0 * a01;
-        const double q = h * h + b2 * b2;
-        if (q > 1e-290) {
-            const double w = q * fast_rsqrt(q);
-            const double cx = fabs(h) + w, sx = (h >= 0 ? -b2 : b2);
-            const double r2 = fast_rsqrt(cx * cx + sx * sx);
-            c2 = cx * r2;
-            s2 = sx * r2;
-        }
-    }
-    const double cl = c2 * c1 + s2 * s1, sl = c2 * s1 - s2 * c1;
-#pragma unroll
-    for (int j = 0; j < 3; ++j) {  // rows (Q,P) <- L * rows
-        const double x = W[Q][j], y = W[P][j];
-        W[Q][j] = cl * x + sl * y;
-        W[P][j] = -sl * x + cl * y;
-    }
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {  // cols (Q,P) <- cols * J ; U <- U L^T ; V <- V J
-        double x = W[i][Q], y = W[i][P];
-        W[i][Q] = c2 * x - s2 * y;
-        W[i][P] = s2 * x + c2 * y;
-        x = U[i][Q];
-        y = U[i][P];
-        U[i][Q] = cl * x + sl * y;
-        U[i][P] = -sl * x + cl * y;
-        x = V[i][Q];
-        y = V[i][P];
-        V[i][Q] = c2 * x - s2 * y;
-        V[i][P] = s2 * x + c2 * y;
-    }
-    maxdiag = fmax(maxdiag, fmax(fabs(W[P][P]), fabs(W[Q][Q])));
-}
-
-template <int I, int K>
-__device__ __forceinline__ void swap_cols(double (&S)[3], double (&U)[3][3], double (&V)[3][3]) {
-    double t = S[I];
-    S[I] = S[K];
-    S[K] = t;
-#pragma unroll
-    for (int r = 0; r < 3; ++r) {
-        t = U[r][I]; U[r][I] = U[r][K]; U[r][K] = t;
-        t = V[r][I]; V[r][I] = V[r][K]; V[r][K] = t;
-    }
-}
-
-__device__ __forceinline__ double det3(const double (&M)[3][3]) {
-    return M[0][0] * (M[1][1] * M[2][2] - M[1][2] * M[2][1]) - M[0][1] * (M[1][0] * M[2][2] - M[1][2] * M[2][0]) +
-           M[0][2] * (M[1][0] * M[2][1] - M[1][1] * M[2][0]);
-}
-
-// Kabsch rotation of a 3x3 covariance (Eigen umeyama without scaling): R = U diag(1,1,s) V^T.
-// warm (18 doubles: U then V, row-major) carries the singular vectors of the previous ICP
-// iteration of the same tile: W = U^T sigma V is then already nearly diagonal and the Jacobi
-// iteration converges in about two sweeps instead of six.  warm is updated in place.
-// (No pre-scaling by max|sigma|: the convergence threshold is relative and covariances of
-// metre-scale clouds are nowhere near the float64 range limits.)
-__device__ void kabsch_rotation(const double (&sigma)[3][3], double (&R)[3][3], double *warm, bool have_warm) {
-    double W[3][3], U[3][3], V[3][3];
-    if (have_warm) {
-        double SV[3][3];
-#pragma unroll
-        for (int i = 0; i < 3; ++i)
-#pragma unroll
-            for (int j = 0; j < 3; ++j) {
-                U[i][j] = warm[3 * i + j];
-                V[i][j] = warm[9 + 3 * i + j];
-            }
-#pragma unroll
-        for (int i = 0; i < 3; ++i)
-#pragma unroll
-            for (int j = 0; j < 3; ++j) SV[i][j] = sigma[i][0] * V[0][j] + sigma[i][1] * V[1][j] + sigma[i][2] * V[2][j];
-#pragma unroll
-        for (int i = 0; i < 3; ++i)
-#pragma unroll
-            for (int j = 0; j < 3; ++j) W[i][j] = U[0][i] * SV[0][j] + U[1][i] * SV[1][j] + U[2][i] * SV[2][j];
-    } else {
-#pragma unroll
-        for (int i = 0; i < 3; ++i)
-#pragma unroll
-            for (int j = 0; j < 3; ++j) {
-                W[i][j] = sigma[i][j];
-                U[i][j] = V[i][j] = (i == j) ? 1.0 : 0.0;
-            }
-    }
-    double maxdiag = fmax(fabs(W[0][0]), fmax(fabs(W[1][1]), fabs(W[2][2])));
-    bool finished = false;
-    for (int sweep = 0; sweep < 64 && !finished; ++sweep) {
-        finished = true;
-        jacobi_pair<1, 0>(W, U, V, maxdiag, finished);
-        jacobi_pair<2, 0>(W, U, V, maxdiag, finished);
-        jacobi_pair<2, 1>(W, U, V, maxdiag, finished);
-    }
-    double S[3];
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-        const double a = fabs(W[i][i]);
-        S[i] = a;
-        if (a != 0.0 && W[i][i] < 0.0) {
-#pragma unroll
-            for (int r = 0; r < 3; ++r) U[r][i] = -U[r][i];
-        }
-    }
-    // sort descending (3-element network equivalent to Eigen's selection sort)
-    if (S[1] > S[0] && S[1] >= S[2]) swap_cols<0, 1>(S, U, V);
-    else if (S[2] > S[0] && S[2] > S[1]) swap_cols<0, 2>(S, U, V);
-    if (S[2] > S[1]) swap_cols<1, 2>(S, U, V);
-#pragma unroll
-    for (int i = 0; i < 3; ++i)
-#pragma unroll
-        for (int j = 0; j < 3; ++j) {
-            warm[3 * i + j] = U[i][j];
-            warm[9 + 3 * i + j] = V[i][j];
-        }
-    const double sgn = (det3(U) * det3(V) < 0) ? -1.0 : 1.0;
-#pragma unroll
-    for (int r = 0; r < 3; ++r)
-#pragma unroll
-        for (int c = 0; c < 3; ++c) R[r][c] = U[r][0] * V[c][0] + U[r][1] * V[c][1] + sgn * U[r][2] * V[c][2];
-}
-
-// 1/x to ~2^-40: MUFU.RCP64H seed + one Newton step.  Only used inside Newton iterations that
-// self-correct, never for a value that is output.
-__device__ __forceinline__ double fast_rcp(double x) {
-    if (!(fabs(x) > 1e-290 && fabs(x) < 1e290)) return 1.0 / x;
-    double y;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-    y = y * (2.0 - x * y);
-    return y;
-}
-
-// 1/x to ~1 ulp: MUFU.RCP64H seed + two Newton steps (a true division is ~25 dependent
-// instructions; this is ~6).
-__device__ __forceinline__ double rcp_nr2(double x) {
-    if (!(fabs(x) > 1e-290 && fabs(x) < 1e290)) return 1.0 / x;
-    double y;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-    y = y * (2.0 - x * y);
-    y = y + y * (1.0 - x * y);
-    return y;
-}
-
-// Kabsch rotation for the common case, written for a short dependent chain (this is the
-// serial section of every ICP iteration).  The source points are re-posed every iteration, so
-// the optimal rotation R = argmax tr(R^T sigma) is near the identity.  R is optimal and proper
-// iff A = R^T sigma is symmetric positive definite (then R is the polar factor U V^T, which is
-// what umeyama returns when det(sigma) > 0).  Newton on SO(3): with S = sym(A) and
-// k = axial(A - A^T), solve (tr(S) I - S) w = k, rotate by the Cayley transform of w (an exact
-// rotation for any w), repeat; quadratic convergence, 2-4 steps.  Returns false when the result
-// cannot be certified (no convergence, A not positive definite: reflection or rank-deficient
-// input) and the caller falls back to the Jacobi SVD.
-__device__ bool kabsch_rotation_newton(const double (&sigma)[3][3], double (&R)[3][3]) {
-    double A[3][3];
-    double scale = 0.0;
-#pragma unroll
-    for (int i = 0; i < 3; ++i)
-#pragma unroll
-        for (int j = 0; j < 3; ++j) {
-            A[i][j] = sigma[i][j];
-            R[i][j] = (i == j) ? 1.0 : 0.0;
-            scale = fmax(scale, fabs(sigma[i][j]));
-        }
-    if (!(scale > 1e-280 && scale < 1e280)) return false;
-    const double tol = 1e-16 * scale;  // below the rounding floor of A: only exact stationarity exits here
-    bool converged = false;
-    for (int step = 0; step < 8; ++step) {
-        const double kx = A[2][1] - A[1][2], ky = A[0][2] - A[2][0], kz = A[1][0] - A[0][1];
-        if (fmax(fabs(kx), fmax(fabs(ky), fabs(kz))) <= tol) {
-            converged = true;
-            break;
-        }
-        // G = tr(S) I - S (symmetric), S = sym(A)
-        const double s01 = 0.5 * (A[0][1] + A[1][0]), s02 = 0.5 * (A[0][2] + A[2][0]), s12 = 0.5 * (A[1][2] + A[2][1]);
-        const double g00 = A[1][1] + A[2][2], g11 = A[0][0] + A[2][2], g22 = A[0][0] + A[1][1];
-        const double g01 = -s01, g02 = -s02, g12 = -s12;
-        // w = G^-1 k by the adjugate
-        const double c00 = g11 * g22 - g12 * g12, c01 = g02 * g12 - g01 * g22, c02 = g01 * g12 - g02 * g11;
-        const double c11 = g00 * g22 - g02 * g02, c12 = g01 * g02 - g00 * g12, c22 = g00 * g11 - g01 * g01;
-        const double det = g00 * c00 + g01 * c01 + g02 * c02;
-        if (!(fabs(det) > 1e-280)) return false;
-        const double rdet = fast_rcp(det);
-        // v = w / 2
-        const double vx = 0.5 * rdet * (c00 * kx + c01 * ky + c02 * kz);
-        const double vy = 0.5 * rdet * (c01 * kx + c11 * ky + c12 * kz);
-        const double vz = 0.5 * rdet * (c02 * kx + c12 * ky + c22 * kz);
-        const double vv = vx * vx + vy * vy + vz * vz;
-        if (!(vv < 1.0)) return false;  // more than 90 degrees in one step: not the near-identity case
-        // Cayley: E = ((1 - vv) I + 2 v v^T + 2 [v]x) / (1 + vv), an exact rotation
-        const double rden = rcp_nr2(1.0 + vv);
-        const double a = (1.0 - vv) * rden, b2 = 2.0 * rden;
-        double E[3][3];
-        E[0][0] = a + b2 * vx * vx; E[0][1] = b2 * (vx * vy - vz); E[0][2] = b2 * (vx * vz + vy);
-        E[1][0] = b2 * (vx * vy + vz); E[1][1] = a + b2 * vy * vy; E[1][2] = b2 * (vy * vz - vx);
-        E[2][0] = b2 * (vx * vz - vy); E[2][1] = b2 * (vy * vz + vx); E[2][2] = a + b2 * vz * vz;
-        double An[3][3], Rn[3][3];
-#pragma unroll
-        for (int i = 0; i < 3; ++i)
-#pragma unroll
-            for (int j = 0; j < 3; ++j) {
-                An[i][j] = E[0][i] * A[0][j] + E[1][i] * A[1][j] + E[2][i] * A[2][j];  // E^T A
-                Rn[i][j] = R[i][0] * E[0][j] + R[i][1] * E[1][j] + R[i][2] * E[2][j];  // R E
-            }
-#pragma unroll
-        for (int i = 0; i < 3; ++i)
-#pragma unroll
-            for (int j = 0; j < 3; ++j) {
-                A[i][j] = An[i][j];
-                R[i][j] = Rn[i][j];
-            }
-        // quadratic convergence: a step of |v| < 1e-7 leaves an error of ~|v|^2 <= 1e-14
-        if (vv < 1e-14) {
-            converged = true;
-            break;
-        }
-    }
-    if (!converged) return false;
-    // certify the maximum: sym(A) positive definite with a margin (Sylvester), which also
-    // rejects det(sigma) <= 0 and near rank-deficient covariances
-    const double m1 = A[0][0];
-    const double m2 = A[0][0] * A[1][1] - A[0][1] * A[1][0];
-    const double m3 = det3(A);
-    const double eps = 1e-9;
-    return m1 > eps * scale && m2 > eps * scale * scale && m3 > eps * scale * scale * scale;
-}
-
-// ------------------------------------------------------------------------------------------
 // 4. fused per-tile ICP
 // ------------------------------------------------------------------------------------------
-struct IcpParams {
-    const void *src;
-    int pts_dtype;
-    const int *src_off;
-    const double *init_T;
-    double r2;
-    int max_iter;
-    double rel_fit, rel_rmse;
-    int ori_only;
-    const double *qx, *qy, *qz;
-    const int *qi;
-    const long long *toff;
-    const int *cnt;
-    const int *status_int;
-    double *pspill;
-    int p_cap;  // source points that fit in shared memory
-    double *out_T, *out_world;
-    int *out_corr;
-    double *out_fit, *out_rmse;
-    int *out_iters, *out_ntgt;
-    long long *dbg_clock;  // optional: per-phase cycle stamps of tile 0 (debug builds of the bench only)
-};
-
-// x' = ((m0 x + m1 y) + m2 z) + m3, each operation rounded (open3d PointCloud::Transform)
-__device__ __forceinline__ double affine_row(const double *m, double x, double y, double z) {
-    return __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(m[0], x), __dmul_rn(m[1], y)), __dmul_rn(m[2], z)), m[3]);
-}
-
-__device__ __forceinline__ void transform_point(const double *T, bool affine, double &x, double &y, double &z) {
-    const double nx = affine_row(T, x, y, z), ny = affine_row(T + 4, x, y, z), nz = affine_row(T + 8, x, y, z);
-    if (affine) {  // last row (0,0,0,1): w == 1 exactly, the division is a bit-exact no-op
-        x = nx; y = ny; z = nz;
-    } else {
-        const double w = affine_row(T + 12, x, y, z);
-        x = nx / w; y = ny / w; z = nz / w;
-    }
-}
-
 // Sum 16 per-lane values over the 32 lanes of a warp with 16 shuffles (a transposing
 // butterfly: every step halves the number of values a lane carries).  Afterwards v[0] holds
 // the warp total of value number (lane >> 1).
@@ -644,6 +340,7 @@ icp_tiles_kernel(const IcpParams p) {
     const int ns = min(ns_tile, lo + per) - lo;
     const int nt = p.cnt[b];
     const long long q0 = p.toff[b];
+    if (p.small_on && tile_is_small(ns_tile, nt)) return;   // icp_small_kernel owns this tile (whole cluster leaves)
     const bool resident = nt <= kQChunk;
     const int nchunks = (nt + kQChunk - 1) / kQChunk;
 
@@ -1083,7 +780,22 @@ extern "C" size_t aurdf_icp_workspace_bytes(int32_t n_tiles, int64_t total_src_p
 static long long *g_dbg_clock = nullptr;
 extern "C" __attribute__((visibility("default"))) void aurdf_debug_set_clock_buffer(void *p) { g_dbg_clock = (long long *)p; }
 
-extern "C" int aurdf_icp_sweep_launches(void) { return 4; }
+namespace aurdf {
+int launch_icp_small(const IcpParams &P, int n_tiles, int variant, cudaStream_t stream);
+}
+
+// AURDF_ICP_SMALL = 0 (general kernel only) | 128 (default) | 256: CTA width of icp_small_kernel
+static int small_variant() {
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("AURDF_ICP_SMALL");
+        v = e ? atoi(e) : 128;
+        if (v != 0 && v != 256) v = 128;
+    }
+    return v;
+}
+
+extern "C" int aurdf_icp_sweep_launches(void) { return small_variant() ? 5 : 4; }
 
 // ---- optional live timing of the dominant kernel (icp_tiles_kernel) --------------------------
 namespace {
@@ -1183,11 +895,18 @@ extern "C" int aurdf_icp_sweep(const void *src_xyz, int pts_dtype, const int32_t
     P.out_T = out_T; P.out_world = out_world_xyz; P.out_corr = out_corr; P.out_fit = out_fitness;
     P.out_rmse = out_rmse; P.out_iters = out_iters; P.out_ntgt = out_ntgt;
     P.dbg_clock = g_dbg_clock;
+    P.small_on = small_variant() != 0;
     EvPair ev{nullptr, nullptr};
     if (g_prof_on) {
         AURDF_CUDA_CHECK(cudaEventCreate(&ev.a));
         AURDF_CUDA_CHECK(cudaEventCreate(&ev.b));
         AURDF_CUDA_CHECK(cudaEventRecord(ev.a, stream));
+    }
+    // small tiles first (one CTA each, all resident at once); the general kernel's CTAs for those
+    // tiles exit immediately, and vice versa
+    if (P.small_on) {
+        const int rc = launch_icp_small(P, n_tiles, small_variant(), stream);
+        if (rc != AURDF_OK) return rc;
     }
     if (use_cluster) {
         cudaLaunchConfig_t cfg = {};

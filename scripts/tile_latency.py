@@ -60,7 +60,10 @@ first, rest = c[0], c[1:]
 k = (len(rest)) // 7
 st = rest[:7 * k].reshape(k, 7)
 print("iterations stamped", k)
-names = ["compose + P update", "NN scan", "S-merge + moment sums", "warp_sum16 + store (pass done)", "barrier A wait", "totals + pose fit (lane 0)"]
+if os.environ.get("AURDF_ICP_SMALL", "128") == "0":
+    names = ["compose + P update", "NN scan", "S-merge + moment sums", "warp_sum16 + store (pass done)", "barrier A wait", "totals + pose fit (lane 0)"]
+else:   # icp_small_kernel
+    names = ["compose + P update", "NN scan + merge + exact distance", "barrier 1 wait", "moment reduction", "barrier 2 wait", "pose fit (lane 0)"]
 for i, nme in enumerate(names):
     print("%-34s: median %d cycles" % (nme, np.median(st[:, i + 1] - st[:, i])))
 print("%-34s: median %d" % ("barrier B + loop overhead", np.median(st[1:, 0] - st[:-1, 6])))

@@ -45,7 +45,7 @@ def test_argument_validation_without_a_device(lib):
     assert L.aurdf_dq_op(0, None, None, None, None, 0, 0, None) == lib.OK          # n == 0: nothing to do
     assert L.aurdf_se3_apply(None, None, None, 0, 0, 0, None, None) == lib.OK
     assert L.aurdf_nn_l2(None, None, None, None, 1, 0, 0, None, None, None) == lib.OK
-    assert L.aurdf_icp_sweep_launches() == 4
+    assert L.aurdf_icp_sweep_launches() in (4, 5)   # 5 with the small-tile kernel (default)
 
 
 def test_missing_library_fails_loudly(lib, monkeypatch, tmp_path):
