@@ -3,8 +3,10 @@
 // aurdf_icp_sweep_host() is what a reference-side binding calls from the numpy world of
 // AutoURDF PointCloud/mlp_reg.py:325: all pointers are HOST pointers.  A context owns one
 // stream, one pinned staging buffer per direction and growable device buffers, so a call is
-//   pack inputs into pinned memory -> ONE async H2D copy -> 4 kernels -> ONE async D2H copy
-//   -> stream synchronise -> unpack.
+//   pack inputs into pinned memory -> async H2D copies -> kernels -> async D2H copies
+//   -> stream synchronise -> unpack,
+// cut into up to 3 contiguous frame blocks on separate streams so that the copies of one block
+// overlap the kernels of another (AURDF_HOST_CHUNKS=1 restores the single-block behaviour).
 // The compacted-target capacity is guessed from the previous call and the call is re-run
 // once (inputs already resident) if the guess was too small.
 #include <stdlib.h>
@@ -13,14 +15,16 @@
 #include "common.cuh"
 
 struct aurdf_ctx {
+    static constexpr int kMaxChunks = 4;
     int device = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t streams[kMaxChunks] = {nullptr, nullptr, nullptr, nullptr};
     void *d_in = nullptr;  size_t d_in_bytes = 0;
     void *d_out = nullptr; size_t d_out_bytes = 0;
     void *d_ws = nullptr;  size_t d_ws_bytes = 0;
     void *h_in = nullptr;  size_t h_in_bytes = 0;
     void *h_out = nullptr; size_t h_out_bytes = 0;
-    int64_t cap_hint = 0;
+    int64_t cap_hint[kMaxChunks] = {0, 0, 0, 0};   // compacted-target capacity that fitted last time, per chunk
+    int cap_chunks = 0, cap_tiles = 0;             // the call shape those hints belong to
     int64_t last_h2d = 0, last_d2h = 0;
 };
 
@@ -66,7 +70,7 @@ extern "C" int aurdf_ctx_create(int device, aurdf_ctx **out) {
     AURDF_CUDA_CHECK(cudaSetDevice(device));
     aurdf_ctx *c = new aurdf_ctx();
     c->device = device;
-    cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    cudaError_t e = cudaStreamCreateWithFlags(&c->streams[0], cudaStreamNonBlocking);
     if (e != cudaSuccess) { delete c; return aurdf::cuda_fail(e, "cudaStreamCreateWithFlags"); }
     *out = c;
     return AURDF_OK;
@@ -75,7 +79,8 @@ extern "C" int aurdf_ctx_create(int device, aurdf_ctx **out) {
 extern "C" void aurdf_ctx_destroy(aurdf_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->device);
-    if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
+    for (cudaStream_t st : c->streams)
+        if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
     if (c->d_in) cudaFree(c->d_in);
     if (c->d_out) cudaFree(c->d_out);
     if (c->d_ws) cudaFree(c->d_ws);
@@ -134,7 +139,7 @@ extern "C" int aurdf_icp_sweep_host(aurdf_ctx *c, const void *src_xyz, int pts_d
     o = 0;
     const size_t q_T = take((size_t)n_tiles * 16 * 8), q_world = take((size_t)n_src * 3 * 8);
     const size_t q_corr = take((size_t)n_src * 4), q_fit = take((size_t)n_tiles * 8), q_rmse = take((size_t)n_tiles * 8);
-    const size_t q_it = take((size_t)n_tiles * 4), q_nt = take((size_t)n_tiles * 4), q_status = take(16);
+    const size_t q_it = take((size_t)n_tiles * 4), q_nt = take((size_t)n_tiles * 4), q_status = take(16 * aurdf_ctx::kMaxChunks);
     const size_t out_bytes = o;
 
     int rc;
@@ -143,82 +148,176 @@ extern "C" int aurdf_icp_sweep_host(aurdf_ctx *c, const void *src_xyz, int pts_d
     if ((rc = grow_dev(&c->d_in, &c->d_in_bytes, in_bytes)) != AURDF_OK) return rc;
     if ((rc = grow_dev(&c->d_out, &c->d_out_bytes, out_bytes)) != AURDF_OK) return rc;
 
-    // host -> device: pinned caller buffers are copied straight from where they are; pageable
-    // ones are packed into the context's pinned staging buffer first
+    // ---- chunks: contiguous frame blocks, one stream each, so the copies of one block overlap the
+    // kernels of another (tiles are frame-major in every caller of this path; if they are not, or the
+    // batch is small, the call runs as a single block)
+    int n_chunks = 1;
+    {
+        static int want = -1;
+        if (want < 0) {
+            const char *e = getenv("AURDF_HOST_CHUNKS");
+            want = e ? atoi(e) : 3;
+            if (want < 1) want = 1;
+            if (want > aurdf_ctx::kMaxChunks) want = aurdf_ctx::kMaxChunks;
+        }
+        bool sorted = true;
+        for (int b = 1; b < n_tiles && sorted; ++b) sorted = tile_frame[b] >= tile_frame[b - 1];
+        if (sorted && n_tiles >= 64 * want && n_frames >= 2 * want) n_chunks = want;
+    }
+    int t_lo[aurdf_ctx::kMaxChunks + 1];   // tile range of every chunk (whole frames)
+    t_lo[0] = 0;
+    for (int k = 1; k < n_chunks; ++k) {
+        int t = (int)((int64_t)n_tiles * k / n_chunks);
+        while (t < n_tiles && t > 0 && tile_frame[t] == tile_frame[t - 1]) ++t;   // do not split a frame
+        t_lo[k] = t < t_lo[k - 1] ? t_lo[k - 1] : t;
+    }
+    t_lo[n_chunks] = n_tiles;
+    for (int k = 0; k < n_chunks; ++k) {
+        if (!c->streams[k]) AURDF_CUDA_CHECK(cudaStreamCreateWithFlags(&c->streams[k], cudaStreamNonBlocking));
+    }
+    if (c->cap_chunks != n_chunks || c->cap_tiles != n_tiles) {   // remembered capacities belong to another shape
+        for (int k = 0; k < aurdf_ctx::kMaxChunks; ++k) c->cap_hint[k] = 0;
+        c->cap_chunks = n_chunks;
+        c->cap_tiles = n_tiles;
+    }
+
     char *hi = (char *)c->h_in;
     char *di = (char *)c->d_in;
+    char *d_o = (char *)c->d_out;
+    char *ho = (char *)c->h_out;
     c->last_h2d = 0;
     c->last_d2h = 0;
-    auto h2d = [&](size_t off, const void *src, size_t bytes) -> int {
+    // host -> device: pinned caller buffers are copied straight from where they are; pageable
+    // ones are packed into the context's pinned staging buffer first
+    auto h2d = [&](cudaStream_t st, size_t off, const void *base, size_t first, size_t bytes) -> int {
         if (!bytes) return AURDF_OK;
+        const char *src = (const char *)base + first;
         const void *from = src;
-        if (!is_pinned(src)) {
-            memcpy(hi + off, src, bytes);
-            from = hi + off;
+        if (!is_pinned(base)) {
+            memcpy(hi + off + first, src, bytes);
+            from = hi + off + first;
         }
-        AURDF_CUDA_CHECK(cudaMemcpyAsync(di + off, from, bytes, cudaMemcpyHostToDevice, c->stream));
+        AURDF_CUDA_CHECK(cudaMemcpyAsync(di + off + first, from, bytes, cudaMemcpyHostToDevice, st));
         c->last_h2d += (int64_t)bytes;
         return AURDF_OK;
     };
-    if ((rc = h2d(o_src, src_xyz, (size_t)n_src * 3 * psz)) != AURDF_OK) return rc;
-    if ((rc = h2d(o_tgt, tgt_xyz, (size_t)n_tgt * 3 * psz)) != AURDF_OK) return rc;
-    if ((rc = h2d(o_box, box_xyz, (size_t)n_box * 3 * bsz)) != AURDF_OK) return rc;
-    if ((rc = h2d(o_soff, src_off, (size_t)(n_tiles + 1) * 4)) != AURDF_OK) return rc;
-    if ((rc = h2d(o_toff, tgt_off, (size_t)(n_frames + 1) * 4)) != AURDF_OK) return rc;
-    if ((rc = h2d(o_tf, tile_frame, (size_t)n_tiles * 4)) != AURDF_OK) return rc;
-    if (box_xyz && (rc = h2d(o_boff, box_off, (size_t)(n_tiles + 1) * 4)) != AURDF_OK) return rc;
-    if ((rc = h2d(o_init, init_T, (size_t)n_tiles * 16 * 8)) != AURDF_OK) return rc;
-
-    int64_t cap = c->cap_hint > 0 ? c->cap_hint : 4 * n_src + 2 * (int64_t)n_tiles + 1024;
-    if (cap > cap_upper) cap = cap_upper;
-    if (cap < 2) cap = 2;
-    char *d_o = (char *)c->d_out;
-    char *ho = (char *)c->h_out;
     // device -> host targets: straight into pinned caller buffers, through staging otherwise
-    struct Out { void *dst; size_t off, bytes; bool direct; };
-    Out outs[7] = {{out_T, q_T, (size_t)n_tiles * 16 * 8, false},     {out_world_xyz, q_world, (size_t)n_src * 3 * 8, false},
-                   {out_corr, q_corr, (size_t)n_src * 4, false},       {out_fitness, q_fit, (size_t)n_tiles * 8, false},
-                   {out_rmse, q_rmse, (size_t)n_tiles * 8, false},     {out_iters, q_it, (size_t)n_tiles * 4, false},
-                   {out_ntgt, q_nt, (size_t)n_tiles * 4, false}};
-    for (Out &o_ : outs) o_.direct = o_.bytes && is_pinned(o_.dst);
-    for (int attempt = 0; attempt < 2; ++attempt) {
-        const size_t ws = aurdf_icp_workspace_bytes(n_tiles, n_src, cap);
-        if ((rc = grow_dev(&c->d_ws, &c->d_ws_bytes, ws)) != AURDF_OK) return rc;
-        rc = aurdf_icp_sweep(di + o_src, pts_dtype, (const int32_t *)(di + o_soff), di + o_tgt,
-                             (const int32_t *)(di + o_toff), (const int32_t *)(di + o_tf),
-                             box_xyz ? (const void *)(di + o_box) : nullptr, box_dtype,
-                             box_xyz ? (const int32_t *)(di + o_boff) : nullptr, (const double *)(di + o_init), n_tiles,
-                             n_src, max_src, box_scale, max_corr_dist, max_iter, rel_fitness, rel_rmse, ori_only,
-                             (double *)(d_o + q_T), (double *)(d_o + q_world), (int32_t *)(d_o + q_corr),
-                             (double *)(d_o + q_fit), (double *)(d_o + q_rmse), (int32_t *)(d_o + q_it),
-                             (int32_t *)(d_o + q_nt), c->d_ws, c->d_ws_bytes, cap, (int32_t *)(d_o + q_status), c->stream);
-        if (rc != AURDF_OK) return rc;
-        // optimistic: queue the status and every output behind the kernels, synchronise once;
-        // if the capacity guess was too small the copies are simply repeated after the re-run
-        AURDF_CUDA_CHECK(cudaMemcpyAsync(ho + q_status, d_o + q_status, 16, cudaMemcpyDeviceToHost, c->stream));
+    struct Out { void *dst; size_t off, per_tile, per_point; bool direct; };
+    Out outs[7] = {{out_T, q_T, 16 * 8, 0, false},   {out_world_xyz, q_world, 0, 3 * 8, false}, {out_corr, q_corr, 0, 4, false},
+                   {out_fitness, q_fit, 8, 0, false}, {out_rmse, q_rmse, 8, 0, false},          {out_iters, q_it, 4, 0, false},
+                   {out_ntgt, q_nt, 4, 0, false}};
+    for (Out &o_ : outs) o_.direct = is_pinned(o_.dst);
+
+    struct Chunk { int t0, t1, f0, f1; int64_t s0, s1, cap, cap_upper; size_t ws_off, ws_bytes; };
+    Chunk ch[aurdf_ctx::kMaxChunks];
+    size_t ws_total = 0;
+    for (int k = 0; k < n_chunks; ++k) {
+        Chunk &q = ch[k];
+        q.t0 = t_lo[k]; q.t1 = t_lo[k + 1];
+        q.s0 = src_off[q.t0]; q.s1 = src_off[q.t1];
+        q.f0 = q.t1 > q.t0 ? tile_frame[q.t0] : 0;
+        q.f1 = q.t1 > q.t0 ? tile_frame[q.t1 - 1] + 1 : 0;
+        if (n_chunks == 1) { q.f0 = 0; q.f1 = n_frames; }
+        q.cap_upper = 0;
+        for (int b = q.t0; b < q.t1; ++b) q.cap_upper += (int64_t)(tgt_off[tile_frame[b] + 1] - tgt_off[tile_frame[b]]) + 1;
+        q.cap = c->cap_hint[k] > 0 ? c->cap_hint[k] : 4 * (q.s1 - q.s0) + 2 * (int64_t)(q.t1 - q.t0) + 1024;
+        if (q.cap > q.cap_upper) q.cap = q.cap_upper;
+        if (q.cap < 2) q.cap = 2;
+        q.ws_bytes = align_up(aurdf_icp_workspace_bytes(q.t1 - q.t0, n_src, q.cap), 256);
+        q.ws_off = ws_total;
+        ws_total += q.ws_bytes;
+    }
+    if ((rc = grow_dev(&c->d_ws, &c->d_ws_bytes, ws_total)) != AURDF_OK) return rc;
+
+    // queue one chunk on its stream: inputs, the four/five kernels, outputs
+    auto run_chunk = [&](int k, bool copy_inputs) -> int {
+        const Chunk &q = ch[k];
+        cudaStream_t st = c->streams[k];
+        const int nt = q.t1 - q.t0;
+        if (nt <= 0) return AURDF_OK;
+        int rc2;
+        if (copy_inputs) {
+            if ((rc2 = h2d(st, o_src, src_xyz, (size_t)q.s0 * 3 * psz, (size_t)(q.s1 - q.s0) * 3 * psz)) != AURDF_OK) return rc2;
+            if ((rc2 = h2d(st, o_tgt, tgt_xyz, (size_t)tgt_off[q.f0] * 3 * psz, (size_t)(tgt_off[q.f1] - tgt_off[q.f0]) * 3 * psz)) != AURDF_OK) return rc2;
+            if (box_xyz) {
+                if ((rc2 = h2d(st, o_box, box_xyz, (size_t)box_off[q.t0] * 3 * bsz, (size_t)(box_off[q.t1] - box_off[q.t0]) * 3 * bsz)) != AURDF_OK) return rc2;
+                if ((rc2 = h2d(st, o_boff, box_off, (size_t)q.t0 * 4, (size_t)(nt + 1) * 4)) != AURDF_OK) return rc2;
+            }
+            if ((rc2 = h2d(st, o_soff, src_off, (size_t)q.t0 * 4, (size_t)(nt + 1) * 4)) != AURDF_OK) return rc2;
+            if ((rc2 = h2d(st, o_toff, tgt_off, (size_t)q.f0 * 4, (size_t)(q.f1 - q.f0 + 1) * 4)) != AURDF_OK) return rc2;
+            if ((rc2 = h2d(st, o_tf, tile_frame, (size_t)q.t0 * 4, (size_t)nt * 4)) != AURDF_OK) return rc2;
+            if ((rc2 = h2d(st, o_init, init_T, (size_t)q.t0 * 16 * 8, (size_t)nt * 16 * 8)) != AURDF_OK) return rc2;
+        }
+        int max_src_c = 0;
+        for (int b = q.t0; b < q.t1; ++b) max_src_c = src_off[b + 1] - src_off[b] > max_src_c ? src_off[b + 1] - src_off[b] : max_src_c;
+        // per-tile arrays are shifted to the chunk's first tile; point arrays keep their base because the
+        // offsets stored in src_off / box_off / tgt_off are global
+        rc2 = aurdf_icp_sweep(di + o_src, pts_dtype, (const int32_t *)(di + o_soff) + q.t0, di + o_tgt,
+                              (const int32_t *)(di + o_toff), (const int32_t *)(di + o_tf) + q.t0,
+                              box_xyz ? (const void *)(di + o_box) : nullptr, box_dtype,
+                              box_xyz ? (const int32_t *)(di + o_boff) + q.t0 : nullptr,
+                              (const double *)(di + o_init) + 16 * (size_t)q.t0, nt, n_src, max_src_c, box_scale,
+                              max_corr_dist, max_iter, rel_fitness, rel_rmse, ori_only,
+                              (double *)(d_o + q_T) + 16 * (size_t)q.t0, (double *)(d_o + q_world), (int32_t *)(d_o + q_corr),
+                              (double *)(d_o + q_fit) + q.t0, (double *)(d_o + q_rmse) + q.t0, (int32_t *)(d_o + q_it) + q.t0,
+                              (int32_t *)(d_o + q_nt) + q.t0, (char *)c->d_ws + q.ws_off, q.ws_bytes, q.cap,
+                              (int32_t *)(d_o + q_status) + 4 * k, st);
+        if (rc2 != AURDF_OK) return rc2;
+        // optimistic: queue the status and every output behind the kernels; if the capacity guess was
+        // too small the chunk is simply run again (inputs already resident)
+        AURDF_CUDA_CHECK(cudaMemcpyAsync(ho + q_status + 16 * k, d_o + q_status + 16 * k, 16, cudaMemcpyDeviceToHost, st));
         c->last_d2h += 16;
         for (Out &o_ : outs) {
-            if (!o_.bytes) continue;
-            AURDF_CUDA_CHECK(cudaMemcpyAsync(o_.direct ? o_.dst : (void *)(ho + o_.off), d_o + o_.off, o_.bytes,
-                                             cudaMemcpyDeviceToHost, c->stream));
-            c->last_d2h += (int64_t)o_.bytes;
+            const size_t first = o_.per_tile ? o_.per_tile * (size_t)q.t0 : o_.per_point * (size_t)q.s0;
+            const size_t bytes = o_.per_tile ? o_.per_tile * (size_t)nt : o_.per_point * (size_t)(q.s1 - q.s0);
+            if (!bytes) continue;
+            AURDF_CUDA_CHECK(cudaMemcpyAsync(o_.direct ? (void *)((char *)o_.dst + first) : (void *)(ho + o_.off + first),
+                                             d_o + o_.off + first, bytes, cudaMemcpyDeviceToHost, st));
+            c->last_d2h += (int64_t)bytes;
         }
-        AURDF_CUDA_CHECK(cudaStreamSynchronize(c->stream));
-        const int32_t *st = (const int32_t *)(ho + q_status);
-        const int64_t need = (int64_t)(uint32_t)st[1] | ((int64_t)st[2] << 32);
-        if (!st[0]) {
-            c->cap_hint = need + need / 8 + 64;  // next call of the same shape fits first time
-            break;
+        return AURDF_OK;
+    };
+
+    for (int k = 0; k < n_chunks; ++k)
+        if ((rc = run_chunk(k, true)) != AURDF_OK) return rc;
+    for (int k = 0; k < n_chunks; ++k) {
+        AURDF_CUDA_CHECK(cudaStreamSynchronize(c->streams[k]));
+        const int32_t *st = (const int32_t *)(ho + q_status + 16 * k);
+        int64_t need = (int64_t)(uint32_t)st[1] | ((int64_t)st[2] << 32);
+        if (ch[k].t1 > ch[k].t0 && st[0]) {   // capacity guess too small: once more with the exact size
+            ch[k].cap = need;
+            const size_t ws = align_up(aurdf_icp_workspace_bytes(ch[k].t1 - ch[k].t0, n_src, need), 256);
+            if (ws > ch[k].ws_bytes) {   // needs a workspace of its own: wait for the other chunks, then regrow
+                for (int j = 0; j < n_chunks; ++j) AURDF_CUDA_CHECK(cudaStreamSynchronize(c->streams[j]));
+                // outputs of the other chunks are already on the host; only this chunk uses the new workspace
+                void *extra = nullptr;
+                cudaError_t e = cudaMalloc(&extra, ws);
+                if (e != cudaSuccess) { aurdf::set_error("cudaMalloc(%zu) failed: %s", ws, cudaGetErrorString(e)); return AURDF_ENOMEM; }
+                const size_t keep_off = ch[k].ws_off, keep_bytes = ch[k].ws_bytes;
+                void *keep_ws = c->d_ws;
+                c->d_ws = extra; ch[k].ws_off = 0; ch[k].ws_bytes = ws;
+                rc = run_chunk(k, false);
+                cudaError_t e2 = cudaStreamSynchronize(c->streams[k]);
+                c->d_ws = keep_ws; ch[k].ws_off = keep_off; ch[k].ws_bytes = keep_bytes;
+                cudaFree(extra);
+                if (rc != AURDF_OK) return rc;
+                AURDF_CUDA_CHECK(e2);
+            } else {
+                if ((rc = run_chunk(k, false)) != AURDF_OK) return rc;
+                AURDF_CUDA_CHECK(cudaStreamSynchronize(c->streams[k]));
+            }
+            st = (const int32_t *)(ho + q_status + 16 * k);
+            if (st[0]) {
+                aurdf::set_error("aurdf_icp_sweep_host: compacted-target capacity %lld still too small", (long long)need);
+                return AURDF_ECAPACITY;
+            }
+            need = (int64_t)(uint32_t)st[1] | ((int64_t)st[2] << 32);
         }
-        if (attempt == 1) {
-            aurdf::set_error("aurdf_icp_sweep_host: compacted-target capacity %lld still too small (need %lld)",
-                             (long long)cap, (long long)need);
-            return AURDF_ECAPACITY;
-        }
-        cap = need;
-        c->last_d2h = 0;
+        c->cap_hint[k] = need + need / 8 + 64;   // next call of the same shape fits first time
     }
-    for (Out &o_ : outs)
-        if (o_.bytes && !o_.direct) memcpy(o_.dst, ho + o_.off, o_.bytes);
+    for (Out &o_ : outs) {
+        const size_t bytes = o_.per_tile ? o_.per_tile * (size_t)n_tiles : o_.per_point * (size_t)n_src;
+        if (bytes && !o_.direct) memcpy(o_.dst, ho + o_.off, bytes);
+    }
     return AURDF_OK;
 }

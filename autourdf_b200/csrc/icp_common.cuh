@@ -105,7 +105,7 @@ __device__ __forceinline__ double det3(const double (&M)[3][3]) {
 // iteration converges in about two sweeps instead of six.  warm is updated in place.
 // (No pre-scaling by max|sigma|: the convergence threshold is relative and covariances of
 // metre-scale clouds are nowhere near the float64 range limits.)
-static __device__ void kabsch_rotation(const double (&sigma)[3][3], double (&R)[3][3], double *warm, bool have_warm) {
+static __device__ __noinline__ void kabsch_rotation(const double (&sigma)[3][3], double (&R)[3][3], double *warm, bool have_warm) {
     double W[3][3], U[3][3], V[3][3];
     if (have_warm) {
         double SV[3][3];
@@ -273,51 +273,62 @@ static __device__ bool kabsch_rotation_newton(const double (&sigma)[3][3], doubl
     return m1 > eps * scale && m2 > eps * scale * scale && m3 > eps * scale * scale * scale;
 }
 
-// Same fixed point as kabsch_rotation_newton, arranged for a small register footprint and for the
-// late ICP iterations that dominate a slow tile (update rotations of 1e-3 rad and below):
-//   * the accumulated rotation is a quaternion: a Cayley step with vector v is the unit quaternion
-//     (1, v)/sqrt(1+v.v), so R = E1 E2 ... is q <- q (x) (1, v) and one conversion at the end;
-//   * A <- E^T A is applied column by column without forming E:
-//     A_j <- a A_j + b (v (v.A_j) - v x A_j),  a = (1-v.v)/(1+v.v),  b = 2/(1+v.v);
+// Raw reciprocal (MUFU.RCP64H seed + Newton) without range checks: inf / NaN inputs propagate and
+// are caught by the caller's final tests.
+__device__ __forceinline__ double rcp_raw1(double x) {   // ~2^-40
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    return y * (2.0 - x * y);
+}
+__device__ __forceinline__ double rcp_raw2(double x) {   // ~1 ulp
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    y = y * (2.0 - x * y);
+    return y + y * (1.0 - x * y);
+}
+
+// Same fixed point as kabsch_rotation_newton, written for the serial section of the small-tile
+// kernel: short code (it is re-fetched every ICP iteration), ~60 live registers, no divisions.
+//   * the accumulated rotation is a quaternion: a Cayley step with vector v is the (unnormalised)
+//     quaternion (1, v), so R = E1 E2 ... is q <- q (x) (1, v) and one conversion at the end;
+//   * A <- (1 + v.v) E^T A is applied column by column without forming E:
+//     A_j <- (1 - v.v) A_j + 2 (v (v.A_j) - v x A_j); the positive factor (1 + v.v) changes neither
+//     the polar factor nor the Newton direction, so it is never divided out;
 //   * a correction with |v| < 1e-8 only enters q (its effect on A is below the rounding floor), and it
 //     reuses the previous adjugate (chord step) when the previous step was already below 1e-5.
-// Typical cost: 1-2 full steps plus one short finish, ~60 live registers.
-static __device__ bool kabsch_rotation_newton3(const double (&sigma)[3][3], double (&R)[3][3]) {
+// Typical late-ICP cost: one full step plus one short finish.  No range checks on the way:
+// degenerate input turns into inf / NaN and fails the final tests, the caller then falls back to
+// the Jacobi SVD.
+static __device__ __forceinline__ bool kabsch_rotation_newton4(const double (&sigma)[3][3], double (&R)[3][3]) {
     double A[3][3];
-    double scale = 0.0;
 #pragma unroll
     for (int i = 0; i < 3; ++i)
 #pragma unroll
-        for (int j = 0; j < 3; ++j) {
-            A[i][j] = sigma[i][j];
-            scale = fmax(scale, fabs(sigma[i][j]));
-        }
-    if (!(scale > 1e-280 && scale < 1e280)) return false;
-    const double tol = 1e-16 * scale;
+        for (int j = 0; j < 3; ++j) A[i][j] = sigma[i][j];
+    const double tol = 1e-16 * (fabs(A[0][0]) + fabs(A[1][1]) + fabs(A[2][2]));
     double qw = 1.0, qx = 0.0, qy = 0.0, qz = 0.0;
     double c00 = 0, c01 = 0, c02 = 0, c11 = 0, c12 = 0, c22 = 0, hrdet = 0;   // adjugate of G, 0.5 / det(G)
-    double vv_prev = 1.0;
+    double vv = 1.0;
     bool converged = false;
+#pragma unroll 1
     for (int step = 0; step < 8; ++step) {
         const double kx = A[2][1] - A[1][2], ky = A[0][2] - A[2][0], kz = A[1][0] - A[0][1];
         if (fmax(fabs(kx), fmax(fabs(ky), fabs(kz))) <= tol) {
             converged = true;
             break;
         }
-        if (!(vv_prev < 1e-10)) {   // full Newton step: G = tr(S) I - S, S = sym(A); chord step otherwise
+        if (!(vv < 1e-10)) {   // full Newton step: G = tr(S) I - S, S = sym(A); chord step otherwise
             const double g01 = -0.5 * (A[0][1] + A[1][0]), g02 = -0.5 * (A[0][2] + A[2][0]), g12 = -0.5 * (A[1][2] + A[2][1]);
             const double g00 = A[1][1] + A[2][2], g11 = A[0][0] + A[2][2], g22 = A[0][0] + A[1][1];
             c00 = g11 * g22 - g12 * g12; c01 = g02 * g12 - g01 * g22; c02 = g01 * g12 - g02 * g11;
             c11 = g00 * g22 - g02 * g02; c12 = g01 * g02 - g00 * g12; c22 = g00 * g11 - g01 * g01;
-            const double det = g00 * c00 + g01 * c01 + g02 * c02;
-            if (!(fabs(det) > 1e-280)) return false;
-            hrdet = 0.5 * fast_rcp(det);
+            hrdet = 0.5 * rcp_raw1(g00 * c00 + g01 * c01 + g02 * c02);
         }
         const double vx = hrdet * (c00 * kx + c01 * ky + c02 * kz);
         const double vy = hrdet * (c01 * kx + c11 * ky + c12 * kz);
         const double vz = hrdet * (c02 * kx + c12 * ky + c22 * kz);
-        const double vv = vx * vx + vy * vy + vz * vz;
-        if (!(vv < 1.0)) return false;   // more than 90 degrees in one step: not the near-identity case
+        vv = vx * vx + vy * vy + vz * vz;
+        if (!(vv < 1.0)) return false;   // more than 90 degrees in one step (or NaN): not the near-identity case
         {   // q <- q (x) (1, v)
             const double w = qw, x = qx, y = qy, z = qz;
             qw = w - (x * vx + y * vy + z * vz);
@@ -329,32 +340,28 @@ static __device__ bool kabsch_rotation_newton3(const double (&sigma)[3][3], doub
             converged = true;
             break;
         }
-        const double rden = rcp_nr2(1.0 + vv);
-        const double a = (1.0 - vv) * rden, b2 = 2.0 * rden;
+        const double omv = 1.0 - vv;
 #pragma unroll
         for (int j = 0; j < 3; ++j) {
             const double m0 = A[0][j], m1 = A[1][j], m2 = A[2][j];
             const double d = vx * m0 + vy * m1 + vz * m2;
-            const double cx = vy * m2 - vz * m1, cy = vz * m0 - vx * m2, cz = vx * m1 - vy * m0;
-            A[0][j] = a * m0 + b2 * (vx * d - cx);
-            A[1][j] = a * m1 + b2 * (vy * d - cy);
-            A[2][j] = a * m2 + b2 * (vz * d - cz);
+            A[0][j] = omv * m0 + 2.0 * (vx * d - (vy * m2 - vz * m1));
+            A[1][j] = omv * m1 + 2.0 * (vy * d - (vz * m0 - vx * m2));
+            A[2][j] = omv * m2 + 2.0 * (vz * d - (vx * m1 - vy * m0));
         }
-        vv_prev = vv;
         if (vv < 1e-13) {   // a step of |v| < 3e-7 leaves a residual of ~|v|^2 <= 1e-13
             converged = true;
             break;
         }
     }
     if (!converged) return false;
-    // certify the maximum: sym(A) positive definite with a margin (Sylvester), which also rejects
-    // det(sigma) <= 0 and near rank-deficient covariances
-    const double m1 = A[0][0];
+    // certify the maximum: sym(A) positive definite with a margin relative to tr(A) (= the nuclear
+    // norm of sigma at the optimum), which also rejects det(sigma) <= 0 and near rank-deficient input
+    const double tr = A[0][0] + A[1][1] + A[2][2];
+    const double e1 = 1e-9 * tr, e2 = e1 * tr, e3 = e2 * tr;
     const double m2 = A[0][0] * A[1][1] - A[0][1] * A[1][0];
-    const double m3 = det3(A);
-    const double eps = 1e-9;
-    if (!(m1 > eps * scale && m2 > eps * scale * scale && m3 > eps * scale * scale * scale)) return false;
-    const double s = 2.0 * rcp_nr2(qw * qw + qx * qx + qy * qy + qz * qz);
+    if (!(A[0][0] > e1 && m2 > e2 && det3(A) > e3)) return false;
+    const double s = 2.0 * rcp_raw2(qw * qw + qx * qx + qy * qy + qz * qz);
     R[0][0] = 1.0 - s * (qy * qy + qz * qz); R[0][1] = s * (qx * qy - qz * qw); R[0][2] = s * (qx * qz + qy * qw);
     R[1][0] = s * (qx * qy + qz * qw); R[1][1] = 1.0 - s * (qx * qx + qz * qz); R[1][2] = s * (qy * qz - qx * qw);
     R[2][0] = s * (qx * qz - qy * qw); R[2][1] = s * (qy * qz + qx * qw); R[2][2] = 1.0 - s * (qx * qx + qy * qy);
@@ -389,7 +396,8 @@ struct IcpParams {
 // are resident per SM (all 900 tiles of wx200_5 start at once): icp_small.cu.  Anything larger
 // runs in the general chunk-streaming / cluster kernel of icp_sweep.cu.
 constexpr int kSmNs = 320;     // most source points of a small tile
-constexpr int kSmNt32 = 768;   // most masked targets of a small tile (float32 copies in shared memory)
+constexpr int kSmPairs = 384;  // float32 target pairs in shared memory, incl. the scan's read-ahead padding
+constexpr int kSmNt32 = 2 * kSmPairs - 8;   // most masked targets of a small tile (760)
 constexpr int kSmNt64 = 384;   // most targets whose float64 copy also lives in shared memory
 __device__ __forceinline__ bool tile_is_small(int ns, int nt) { return ns <= kSmNs && nt <= kSmNt32; }
 

@@ -11,34 +11,36 @@
 //     min/max per pair instead of compare+select chains;
 //   * replaces the per-lane 16-accumulator moment sums and the transposing shuffle reduction by a
 //     shared-memory reduction with one thread group per moment;
-//   * fits the pose with the shortened Newton-on-SO(3) iteration (kabsch_rotation_newton3).
+//   * fits the pose with the shortened Newton-on-SO(3) iteration (kabsch_rotation_newton4).
 // Semantics are those of icp_tiles_kernel (open3d RegistrationICP point-to-point inside
 // masked_icp, cluster_icp.py:118-191): the argmin is certified against float64 or re-done in
 // float64 with the reference's operation order, so correspondences stay bit-identical.
 #include <math.h>
+#include <stdlib.h>
+
+#include <type_traits>
 
 #include "icp_common.cuh"
 
 namespace aurdf {
 
 constexpr uint32_t kIdxMask = 0x3FFu;   // low mantissa bits of a key hold the target index (< 1024)
-static_assert(kSmNt32 <= 1024 && kSmNt32 % 2 == 0, "index field");
+static_assert(2 * kSmPairs <= 1024 && kSmNt32 + 8 <= 2 * kSmPairs, "index field / read-ahead padding");
 
-constexpr size_t kSmallSmemBytes = (size_t)(kSmNt32 / 2) * (sizeof(float4) + sizeof(float2)) +
+constexpr size_t kSmallSmemBytes = (size_t)kSmPairs * (sizeof(float4) + sizeof(float2)) +
                                    (size_t)3 * kSmNt64 * sizeof(double) + (size_t)3 * kSmNs * sizeof(double) +
                                    (size_t)kSmNs * sizeof(double) + (size_t)kSmNs * sizeof(int);
 
-template <int NT, int MINB>
+template <int NT, int MINB, bool DBG>
 __global__ void __launch_bounds__(NT, MINB)
 icp_small_kernel(const IcpParams p) {
     constexpr int kWarps = NT / 32;
-    constexpr int G = NT / 16;   // lanes per moment in the reduction (8 or 16: inside one warp)
-    static_assert(kWarps >= 4 && G <= 32, "thread count");
+    static_assert(kWarps >= 4, "thread count");
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float4 *sxy = reinterpret_cast<float4 *>(smem_raw);             // (-x0, -x1, -y0, -y1) of a target pair
-    float2 *sz = reinterpret_cast<float2 *>(sxy + kSmNt32 / 2);     // (-z0, -z1)
-    double *sqx = reinterpret_cast<double *>(sz + kSmNt32 / 2);     // float64 targets (n_t <= kSmNt64)
+    float2 *sz = reinterpret_cast<float2 *>(sxy + kSmPairs);        // (-z0, -z1)
+    double *sqx = reinterpret_cast<double *>(sz + kSmPairs);        // float64 targets (n_t <= kSmNt64)
     double *sqy = sqx + kSmNt64;
     double *sqz = sqy + kSmNt64;
     double *spx = sqz + kSmNt64;                                    // current source points
@@ -47,8 +49,8 @@ icp_small_kernel(const IcpParams p) {
     double *sbd = spz + kSmNs;                                      // exact squared distance to the match
     int *scj = reinterpret_cast<int *>(sbd + kSmNs);                // match (compacted index) or -1
 
-    __shared__ double s_tot[16];   // moment totals of the current pass
-    __shared__ int s_cnt;          // inlier count of the current pass
+    __shared__ double s_part[kWarps][4][6];   // per-warp moment products M[0..3][0..5] of the current pass
+    __shared__ double s_tot[16];              // their totals, M[r][c] at 4 r + c (fit warp only)
     __shared__ double s_U[16];     // current update (row-major 4x4)
     __shared__ double s_T[16];     // accumulated pose
     __shared__ double s_prev[2];   // fitness, rmse of the previous pass
@@ -110,17 +112,30 @@ icp_small_kernel(const IcpParams p) {
     // float32 filter works in the same frame
     const double ox = nt > 0 ? qxp[0] : 0.0, oy = nt > 0 ? qyp[0] : 0.0, oz = nt > 0 ? qzp[0] : 0.0;
 
-    // float32 copies of the targets, negated (the scan adds), two per entry; an odd tail is padded
-    // with a point no source can match.  aq = largest coordinate magnitude, scales the error bound.
+    // split factor: S lanes share one source point when the tile is narrower than the CTA; the scan
+    // reads up to 4 S pairs past the end (software pipelining), which must stay inside the array
     const int npairs = (nt + 1) >> 1;
+    int S = 1;
+    while (S < 32 && ns * (S * 2) <= NT && npairs + 8 * S <= kSmPairs) S *= 2;
+    const int pts_per_round = NT / S;
+    const int rounds = (ns + pts_per_round - 1) / pts_per_round;
+    const int sub = tid & (S - 1);
+    const int trips2 = ((npairs + S - 1) / S + 1) >> 1;   // scan trips of two pairs per lane
+
+    // float32 copies of the targets, negated (the scan adds), two per entry; the odd tail and the
+    // read-ahead padding are points no source can match.  aq = largest coordinate magnitude, scales
+    // the error bound.
     float aq = 0.f;
     {
         float amax = 0.f;
-        for (int jj = tid; jj < npairs; jj += NT) {
+        const int nfill = min(kSmPairs, npairs + 4 * S);
+        for (int jj = tid; jj < nfill; jj += NT) {
             const int j0 = 2 * jj, j1 = j0 + 1;
-            const float ax = (float)(qxp[j0] - ox), ay = (float)(qyp[j0] - oy), az = (float)(qzp[j0] - oz);
-            float bx = 1e18f, by = 0.f, bz = 0.f;
-            amax = fmaxf(amax, fmaxf(fabsf(ax), fmaxf(fabsf(ay), fabsf(az))));
+            float ax = 1e18f, ay = 0.f, az = 0.f, bx = 1e18f, by = 0.f, bz = 0.f;
+            if (j0 < nt) {
+                ax = (float)(qxp[j0] - ox); ay = (float)(qyp[j0] - oy); az = (float)(qzp[j0] - oz);
+                amax = fmaxf(amax, fmaxf(fabsf(ax), fmaxf(fabsf(ay), fabsf(az))));
+            }
             if (j1 < nt) {
                 bx = (float)(qxp[j1] - ox); by = (float)(qyp[j1] - oy); bz = (float)(qzp[j1] - oz);
                 amax = fmaxf(amax, fmaxf(fabsf(bx), fmaxf(fabsf(by), fabsf(bz))));
@@ -136,16 +151,15 @@ icp_small_kernel(const IcpParams p) {
         for (int w = 0; w < kWarps; ++w) aq = fmaxf(aq, s_amax[w]);
     }
 
-    // split factor: S lanes share one source point when the tile is narrower than the CTA
-    int S = 1;
-    while (S < 32 && ns * (S * 2) <= NT) S *= 2;
-    const int pts_per_round = NT / S;
-    const int rounds = (ns + pts_per_round - 1) / pts_per_round;
-    const int sub = tid & (S - 1);
-
-    long long dbg_n = 0;
-    auto stamp = [&]() {
-        if (p.dbg_clock && blockIdx.x == 0 && tid == 0 && dbg_n < 4096) p.dbg_clock[dbg_n++] = clock64();
+    // debug hook: (clock, id) pairs of thread 0 of tile 0 (scripts/tile_latency.py)
+    int dbg_n = 0;
+    auto stamp = [&](int id) {
+        if constexpr (!DBG) return;
+        if (blockIdx.x == 0 && tid == 0 && dbg_n < 2040) {
+            p.dbg_clock[2 * dbg_n] = clock64();
+            p.dbg_clock[2 * dbg_n + 1] = id;
+            ++dbg_n;
+        }
     };
 
     // ---- phase A: move the points by the current update, find every point's nearest target ----
@@ -162,7 +176,7 @@ icp_small_kernel(const IcpParams p) {
                 if (S > 1) __syncwarp();   // the S lanes of a point have all read the old value
                 if (active && sub == 0) { spx[i] = x; spy[i] = y; spz[i] = z; }
             }
-            if (apply && r == 0) stamp();   // [+1] P update done
+            if (r == 0) stamp(1);   // P update done
             double bd = INFINITY;
             int bj = -1;
             bool need_exact = active && nt > 0;
@@ -173,13 +187,10 @@ icp_small_kernel(const IcpParams p) {
                 const float fx = (float)(x - ox), fy = (float)(y - oy), fz = (float)(z - oz);
                 uint32_t m1 = 0xFFFFFFFFu, m2 = 0xFFFFFFFFu;
                 if (active) {
+                    // two pairs per trip, the next trip's pairs loaded before this trip's arithmetic
+                    // (one warp per scheduler has nothing else to hide the shared-memory latency with)
                     const float2 fx2 = make_float2(fx, fx), fy2 = make_float2(fy, fy), fz2 = make_float2(fz, fz);
-                    uint32_t idx = 2u * (uint32_t)sub;
-                    const uint32_t step = 2u * (uint32_t)S;
-#pragma unroll 4
-                    for (int jj = sub; jj < npairs; jj += S, idx += step) {
-                        const float4 qxy = sxy[jj];
-                        const float2 qz = sz[jj];
+                    auto pair = [&](const float4 qxy, const float2 qz, const uint32_t idx) {
                         const float2 dx = __fadd2_rn(fx2, make_float2(qxy.x, qxy.y));
                         const float2 dy = __fadd2_rn(fy2, make_float2(qxy.z, qxy.w));
                         const float2 dz = __fadd2_rn(fz2, qz);
@@ -191,8 +202,34 @@ icp_small_kernel(const IcpParams p) {
                         const uint32_t lo = min(k0, k1), hi = max(k0, k1);
                         m2 = __vimin3_u32(m2, hi, max(m1, lo));
                         m1 = min(m1, lo);
-                    }
+                    };
+                    // SS > 0: compile-time lane stride (addresses fold into immediates); 0: runtime S
+                    auto scan = [&](auto stride_c) {
+                        constexpr int SS = decltype(stride_c)::value;
+                        const int st = SS ? SS : S;
+                        const float4 *pxy = sxy + sub;
+                        const float2 *pz = sz + sub;
+                        uint32_t idx = 2u * (uint32_t)sub;
+                        const uint32_t step = 2u * (uint32_t)st;
+                        float4 a0 = pxy[0], a1 = pxy[st];
+                        float2 b0 = pz[0], b1 = pz[st];
+#pragma unroll 2
+                        for (int t = 0; t < trips2; ++t) {
+                            pxy += 2 * st;
+                            pz += 2 * st;
+                            const float4 n0 = pxy[0], n1 = pxy[st];
+                            const float2 c0 = pz[0], c1 = pz[st];
+                            pair(a0, b0, idx);
+                            pair(a1, b1, idx + step);
+                            idx += 2u * step;
+                            a0 = n0; a1 = n1; b0 = c0; b1 = c1;
+                        }
+                    };
+                    if (S == 1) scan(std::integral_constant<int, 1>{});
+                    else if (S == 2) scan(std::integral_constant<int, 2>{});
+                    else scan(std::integral_constant<int, 0>{});
                 }
+                if (r == 0) stamp(2);   // float32 scan done
                 for (int o = S >> 1; o > 0; o >>= 1) {
                     const uint32_t om1 = __shfl_xor_sync(0xffffffffu, m1, o), om2 = __shfl_xor_sync(0xffffffffu, m2, o);
                     m2 = __vimin3_u32(m2, om2, max(m1, om1));
@@ -219,6 +256,7 @@ icp_small_kernel(const IcpParams p) {
                     }
                 }
             }
+            if (r == 0) stamp(3);   // merge + certificate + exact distance done
             // exact rescan of the uncertified points of this warp (~1e-3 of them; duplicates always):
             // float64, the reference's operation order, strict '<' in ascending index order
             if (__any_sync(0xffffffffu, need_exact)) {
@@ -235,6 +273,7 @@ icp_small_kernel(const IcpParams p) {
                     if (oj >= 0 && (od < bd || (od == bd && oj < bj) || bj < 0)) { bd = od; bj = oj; }
                 }
             }
+            if (r == 0) stamp(4);   // exact rescan (if any lane of the warp needed it) done
             if (active && sub == 0) {
                 const bool inl = bj >= 0 && bd < p.r2;
                 scj[i] = inl ? bj : -1;
@@ -243,71 +282,78 @@ icp_small_kernel(const IcpParams p) {
         }
     };
 
-    // ---- phase B: the 16 moment sums + inlier count, one group of G lanes per moment ----
-    //   0: sum d^2   1-3: sum a   4-6: sum b   7-15: sum b_r a_c     (a = source, b = matched target,
-    //   both about the origin o)
+    // ---- phase B: moment sums on the FP64 tensor cores ----
+    // The 16 moments + sum d^2 are one small product M = U^T W over the matched pairs, with
+    // U = (1, bx, by, bz) (zero row when the point has no match) and W = (1, ax, ay, az, d^2);
+    // a = source point, b = matched target, both about the origin o.  M[0][0] is the inlier count,
+    // M[0][1..3] = sum a, M[1..3][0] = sum b, M[1..3][1..3] = sum b a^T, M[0][4] = sum d^2.
+    // One mma.m8n8k4.f64 adds four points: A[row][k] = U_row(point k), B[k][col] = W_col(point k).
     auto reduce = [&]() {
-        const int m = tid / G, g = tid % G;
-        const double *pa = nullptr, *pq = nullptr;
-        double oa = 0.0, oq = 0.0;
-        if (m >= 1 && m <= 3) {
-            pa = m == 1 ? spx : (m == 2 ? spy : spz);
-            oa = m == 1 ? ox : (m == 2 ? oy : oz);
-        } else if (m >= 4) {
-            const int rr = m <= 6 ? m - 4 : (m - 7) / 3;
-            pq = rr == 0 ? qxp : (rr == 1 ? qyp : qzp);
-            oq = rr == 0 ? ox : (rr == 1 ? oy : oz);
-            if (m >= 7) {
-                const int cc = (m - 7) % 3;
-                pa = cc == 0 ? spx : (cc == 1 ? spy : spz);
-                oa = cc == 0 ? ox : (cc == 1 ? oy : oz);
-            }
-        }
-        double acc = 0.0;
-        int cnt = 0;
-        for (int i = g; i < ns; i += G) {
-            const int j = scj[i];
-            if (j >= 0) {
-                if (m == 0) {
-                    acc += sbd[i];
-                    ++cnt;
-                } else {
-                    const double a = pa ? pa[i] - oa : 1.0;
-                    const double bq = pq ? pq[j] - oq : 1.0;
-                    acc += a * bq;
-                }
-            }
-        }
+        const int gid = lane >> 2, tig = lane & 3;
+        const double *pu = gid == 1 ? qxp : (gid == 2 ? qyp : qzp);
+        const double *pw = gid == 1 ? spx : (gid == 2 ? spy : (gid == 3 ? spz : sbd));
+        const double oc = gid == 1 ? ox : (gid == 2 ? oy : (gid == 3 ? oz : 0.0));
+        // operand = (value - oc) * mul + add: row/column 0 is the constant 1, rows >= 4 and columns >= 5 are 0
+        const double mul_u = (gid >= 1 && gid < 4) ? 1.0 : 0.0, mul_w = (gid >= 1 && gid < 5) ? 1.0 : 0.0;
+        const double add1 = gid == 0 ? 1.0 : 0.0;
+        // four independent accumulator pairs: the mma latency (~100 cycles) is then paid twice, not
+        // eight times, for a 128-point tile
+        double acc[4][2] = {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}};
+#pragma unroll 1
+        for (int base = 4 * warp; base < ns; base += 16 * kWarps) {
 #pragma unroll
-        for (int o = G >> 1; o > 0; o >>= 1) {
-            acc += __shfl_xor_sync(0xffffffffu, acc, o);
-            cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+            for (int k = 0; k < 4; ++k) {
+                const int i = base + 4 * kWarps * k + tig;
+                const int j = i < ns ? scj[i] : -1;
+                const bool ok = j >= 0;
+                const int ic = ok ? i : 0, jc = ok ? j : 0;
+                double u = (pu[jc] - oc) * mul_u + add1;
+                double w = (pw[ic] - oc) * mul_w + add1;                 // column 4 = d^2 (oc = 0)
+                u = ok ? u : 0.0;                                        // unmatched point: zero row and column entry
+                w = ok ? w : 0.0;                                        // (also discards inf * 0 from its d^2 slot)
+                asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                             : "+d"(acc[k][0]), "+d"(acc[k][1]) : "d"(u), "d"(w));
+            }
         }
-        if (g == 0) {
-            s_tot[m] = acc;
-            if (m == 0) s_cnt = cnt;
+        const double d0 = (acc[0][0] + acc[1][0]) + (acc[2][0] + acc[3][0]);
+        const double d1 = (acc[0][1] + acc[1][1]) + (acc[2][1] + acc[3][1]);
+        // this lane holds M[gid][2 tig] and M[gid][2 tig + 1]
+        if (gid < 4 && tig < 3) {
+            s_part[warp][gid][2 * tig] = d0;
+            s_part[warp][gid][2 * tig + 1] = d1;
         }
+    };
+    // totals over the warps' partial products, for consumer warp 0 (the fit) after barrier 2
+    auto gather_totals = [&]() {
+        if (lane < 16) {
+            double t = s_part[0][lane >> 2][lane & 3];
+#pragma unroll
+            for (int w = 1; w < kWarps; ++w) t += s_part[w][lane >> 2][lane & 3];
+            s_tot[lane] = t;
+        }
+        __syncwarp();
     };
 
     // Kabsch / umeyama update from the totals (one lane)
     bool have_warm = false;
     auto fit_pose = [&]() {
-        const double *t = s_tot;
-        const int c = s_cnt;
+        const double *t = s_tot;   // t[4 r + c] = sum u_r w_c
         double Um[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
-        if (c > 0) {
-            const double inv = rcp_nr2((double)c);
+        if (t[0] > 0.0) {
+            const double inv = rcp_raw2(t[0]);
             const double ma[3] = {t[1] * inv, t[2] * inv, t[3] * inv};
-            const double mb[3] = {t[4] * inv, t[5] * inv, t[6] * inv};
+            const double mb[3] = {t[4] * inv, t[8] * inv, t[12] * inv};
             double sigma[3][3], R[3][3];
 #pragma unroll
             for (int r = 0; r < 3; ++r)
 #pragma unroll
-                for (int cc = 0; cc < 3; ++cc) sigma[r][cc] = t[7 + 3 * r + cc] * inv - mb[r] * ma[cc];
-            if (!kabsch_rotation_newton3(sigma, R)) {
+                for (int cc = 0; cc < 3; ++cc) sigma[r][cc] = t[4 * (r + 1) + cc + 1] * inv - mb[r] * ma[cc];
+            stamp(20);   // totals loaded, covariance formed
+            if (!kabsch_rotation_newton4(sigma, R)) {
                 kabsch_rotation(sigma, R, s_warm, have_warm);   // reflection / rank-deficient / large step
                 have_warm = true;
             }
+            stamp(21);   // rotation fitted
             const double mua[3] = {ma[0] + ox, ma[1] + oy, ma[2] + oz};
             const double mub[3] = {mb[0] + ox, mb[1] + oy, mb[2] + oz};
 #pragma unroll
@@ -334,51 +380,45 @@ icp_small_kernel(const IcpParams p) {
         if (lane < 16) s_T[lane] = v;
     };
 
-    stamp();
-    pass(false);
-    __syncthreads();
-    reduce();
-    __syncthreads();
-    if (warp == 0) {
-        if (lane == 0 && p.max_iter > 0) fit_pose();
-    } else if (warp == 1) {
-        if (lane == 0) {
-            const int c = s_cnt;
-            s_prev[0] = c > 0 ? (double)c / (double)ns : 0.0;
-            s_prev[1] = c > 0 ? sqrt(s_tot[0] / (double)c) : 0.0;
-        }
-    }
-    __syncthreads();
-
+    // it = -1 is open3d's initial correspondence pass (no update applied); one copy of every phase
+    // keeps the loop body small enough for the instruction caches.
     int iters = 0;
-    for (int it = 0; it < p.max_iter; ++it) {
-        stamp();   // [7k+0] iteration start
-        if (warp == kWarps - 1) compose_pose();   // uses s_U of this iteration; its next write is after barrier 2
-        pass(true);
-        stamp();   // [+2] NN done
+#pragma unroll 1
+    for (int it = -1; it < p.max_iter; ++it) {
+        const bool apply = it >= 0;
+        stamp(0);   // iteration start
+        if (apply && warp == kWarps - 1) compose_pose();   // uses s_U of this iteration; its next write is after barrier 2
+        pass(apply);
+        stamp(5);   // pass done
         __syncthreads();   // barrier 1: matches and moved points visible
-        stamp();   // [+3]
+        stamp(6);
         reduce();
-        stamp();   // [+4] moment sums done
+        stamp(7);   // moment sums done
         __syncthreads();   // barrier 2: totals visible
-        stamp();   // [+5]
+        stamp(8);
         if (warp == 0) {
             // speculative: the fit for iteration it+1 runs while warp 1 decides whether to stop
+            gather_totals();
             if (lane == 0 && it + 1 < p.max_iter) fit_pose();
         } else if (warp == 1) {
             if (lane == 0) {
-                const int c = s_cnt;
+                double cnt = s_part[0][0][0], d2 = s_part[0][0][4];
+#pragma unroll
+                for (int w = 1; w < kWarps; ++w) { cnt += s_part[w][0][0]; d2 += s_part[w][0][4]; }
+                const int c = (int)cnt;
                 const double fit = c > 0 ? (double)c / (double)ns : 0.0;
-                const double rmse = c > 0 ? sqrt(s_tot[0] / (double)c) : 0.0;
-                s_stop = (fabs(s_prev[0] - fit) < p.rel_fit && fabs(s_prev[1] - rmse) < p.rel_rmse) ? 1 : 0;
+                const double rmse = c > 0 ? sqrt(d2 / (double)c) : 0.0;
+                s_stop = (apply && fabs(s_prev[0] - fit) < p.rel_fit && fabs(s_prev[1] - rmse) < p.rel_rmse) ? 1 : 0;
                 s_prev[0] = fit;
                 s_prev[1] = rmse;
             }
         }
-        stamp();   // [+6] fit done
+        stamp(9);   // fit done, update stored
         __syncthreads();   // barrier 3: update and stop flag visible
-        iters = it + 1;
-        if (s_stop) break;
+        if (apply) {
+            iters = it + 1;
+            if (s_stop) break;
+        }
     }
     __syncthreads();
 
@@ -409,21 +449,38 @@ icp_small_kernel(const IcpParams p) {
 }
 
 // host side: launch over all tiles (CTAs of other classes exit at once)
-int launch_icp_small(const IcpParams &P, int n_tiles, int variant, cudaStream_t stream) {
+template <int NT, int MINB, bool DBG>
+static int launch_variant(const IcpParams &P, int n_tiles, cudaStream_t stream) {
     static bool configured[64] = {};
     int dev = 0;
     AURDF_CUDA_CHECK(cudaGetDevice(&dev));
     if (dev >= 0 && dev < 64 && !configured[dev]) {
-        // 7 x (29.3 KB + static) per SM only fits with the carve-out at its maximum
-        AURDF_CUDA_CHECK(cudaFuncSetAttribute(icp_small_kernel<128, 7>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        AURDF_CUDA_CHECK(cudaFuncSetAttribute(icp_small_kernel<256, 4>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        // MINB x (29.3 KB + static) per SM only fits with the carve-out at its maximum
+        AURDF_CUDA_CHECK(cudaFuncSetAttribute(icp_small_kernel<NT, MINB, DBG>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         configured[dev] = true;
     }
-    if (variant == 256)
-        icp_small_kernel<256, 4><<<n_tiles, 256, kSmallSmemBytes, stream>>>(P);
-    else
-        icp_small_kernel<128, 7><<<n_tiles, 128, kSmallSmemBytes, stream>>>(P);
+    icp_small_kernel<NT, MINB, DBG><<<n_tiles, NT, kSmallSmemBytes, stream>>>(P);
     return AURDF_OK;
 }
 
+int launch_icp_small(const IcpParams &P, int n_tiles, cudaStream_t stream) {
+    static int minb = -1;   // tuning knob: AURDF_ICP_SMALL_MINB = resident CTAs per SM the kernel is compiled for
+    if (minb < 0) {
+        const char *e = getenv("AURDF_ICP_SMALL_MINB");
+        minb = e ? atoi(e) : 6;
+    }
+    if (P.dbg_clock) return launch_variant<128, 5, true>(P, n_tiles, stream);
+    if (minb == 7) return launch_variant<128, 7, false>(P, n_tiles, stream);
+    if (minb == 5) return launch_variant<128, 5, false>(P, n_tiles, stream);
+    return launch_variant<128, 6, false>(P, n_tiles, stream);   // measured best on wx200_5 / franka / allegro_hand
+}
+
 }  // namespace aurdf
+
+// debug: resident CTAs per SM the runtime grants the 128-thread / 7-per-SM variant
+extern "C" __attribute__((visibility("default"))) int aurdf_debug_small_occupancy(void) {
+    int n = -1;
+    cudaFuncSetAttribute(aurdf::icp_small_kernel<128, 6, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, aurdf::icp_small_kernel<128, 6, false>, 128, aurdf::kSmallSmemBytes);
+    return n;
+}

@@ -781,16 +781,15 @@ static long long *g_dbg_clock = nullptr;
 extern "C" __attribute__((visibility("default"))) void aurdf_debug_set_clock_buffer(void *p) { g_dbg_clock = (long long *)p; }
 
 namespace aurdf {
-int launch_icp_small(const IcpParams &P, int n_tiles, int variant, cudaStream_t stream);
+int launch_icp_small(const IcpParams &P, int n_tiles, cudaStream_t stream);
 }
 
-// AURDF_ICP_SMALL = 0 (general kernel only) | 128 (default) | 256: CTA width of icp_small_kernel
+// AURDF_ICP_SMALL = 0: general kernel only (A/B measurements); anything else: small tiles go to icp_small_kernel
 static int small_variant() {
     static int v = -1;
     if (v < 0) {
         const char *e = getenv("AURDF_ICP_SMALL");
-        v = e ? atoi(e) : 128;
-        if (v != 0 && v != 256) v = 128;
+        v = (e && atoi(e) == 0) ? 0 : 1;
     }
     return v;
 }
@@ -905,7 +904,7 @@ extern "C" int aurdf_icp_sweep(const void *src_xyz, int pts_dtype, const int32_t
     // small tiles first (one CTA each, all resident at once); the general kernel's CTAs for those
     // tiles exit immediately, and vice versa
     if (P.small_on) {
-        const int rc = launch_icp_small(P, n_tiles, small_variant(), stream);
+        const int rc = launch_icp_small(P, n_tiles, stream);
         if (rc != AURDF_OK) return rc;
     }
     if (use_cluster) {

@@ -55,6 +55,22 @@ lib.aurdf_debug_set_clock_buffer(buf.data_ptr())
 timeit(one, 10000, reps=1)
 lib.aurdf_debug_set_clock_buffer(None)
 c = buf.cpu().numpy()
+if os.environ.get("AURDF_ICP_SMALL", "128") != "0":
+    # icp_small_kernel: (clock, id) pairs of thread 0 of tile 0
+    ids = {0: "iteration start", 1: "P update", 2: "float32 scan", 3: "merge+certificate+exact distance", 4: "exact rescan branch",
+           5: "pass end", 6: "barrier 1", 7: "moment reduction", 8: "barrier 2", 20: "totals+covariance", 21: "rotation fit",
+           9: "translation+store U (fit done)"}
+    c = c.reshape(-1, 2)
+    c = c[c[:, 0] > 0]
+    from collections import OrderedDict
+    d = OrderedDict()
+    for k in range(1, len(c)):
+        d.setdefault((int(c[k - 1, 1]), int(c[k, 1])), []).append(int(c[k, 0] - c[k - 1, 0]))
+    for (a_, b_), v in d.items():
+        print("%-22s -> %-34s: median %6d  p90 %6d  n %d" % (ids.get(a_, a_), ids.get(b_, b_), np.median(v), np.percentile(v, 90), len(v)))
+    it0 = c[c[:, 1] == 0, 0]
+    print("whole iteration: median %d cycles" % np.median(np.diff(it0)))
+    sys.exit(0)
 c = c[c > 0]
 first, rest = c[0], c[1:]
 k = (len(rest)) // 7
