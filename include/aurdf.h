@@ -216,6 +216,21 @@ enum {
 AURDF_API int aurdf_dq_op(int op, const void *in0, const void *in1, void *out0, void *out1, int64_t n,
                 int dtype, aurdf_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------
+ * Pairwise cluster motion-distance map: replaces CoordMap.coord_dist_map,
+ * PointCloud/coord_map.py:230-307 (T x K x K Python loops, one roma call per element).
+ *   matrices   (n_frames, n_coords, 4, 4) row-major doubles: the stacked matrix/{t:04}.npy files
+ *              the registration loop writes (mlp_reg.py:331)
+ *   diff != 0  motion between consecutive frames (n_frames - 1 steps, :253-286); diff == 0: poses
+ *              themselves (:287-302)
+ *   out_map    (n_coords, n_coords, steps) doubles, step fastest (np.stack(..., axis=2), :304)
+ *   out_sum    (n_coords, n_coords): sum over steps of |out_map| (:305)
+ * n_coords <= 384. workspace: aurdf_coord_dist_map_workspace_bytes() bytes, 256-byte aligned. */
+AURDF_API size_t aurdf_coord_dist_map_workspace_bytes(int32_t n_frames, int32_t n_coords, int32_t diff);
+AURDF_API int aurdf_coord_dist_map(const double *matrices, int32_t n_frames, int32_t n_coords, double bounding_box,
+                         int32_t diff, double *out_map, double *out_sum, void *workspace, size_t workspace_bytes,
+                         aurdf_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
