@@ -390,6 +390,7 @@ struct IcpParams {
     int *out_iters, *out_ntgt;
     long long *dbg_clock;  // optional: per-phase cycle stamps of tile 0 (debug builds of the bench only)
     int small_on;          // small tiles are taken by icp_small_kernel, the general kernel skips them
+    int split_tail;        // icp_small_kernel: widen the lane split of a tile's last, partly filled round
 };
 
 // Tile classes.  A "small" tile keeps its whole state in < 30 KB of shared memory, so that 7 tiles

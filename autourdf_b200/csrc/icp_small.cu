@@ -27,7 +27,7 @@ namespace aurdf {
 constexpr uint32_t kIdxMask = 0x3FFu;   // low mantissa bits of a key hold the target index (< 1024)
 static_assert(2 * kSmPairs <= 1024 && kSmNt32 + 8 <= 2 * kSmPairs, "index field / read-ahead padding");
 
-constexpr size_t kSmallSmemBytes = (size_t)kSmPairs * (sizeof(float4) + sizeof(float2)) +
+constexpr size_t kSmallSmemBytes = (size_t)kSmPairs * (sizeof(float4) + sizeof(float4)) +
                                    (size_t)3 * kSmNt64 * sizeof(double) + (size_t)3 * kSmNs * sizeof(double) +
                                    (size_t)kSmNs * sizeof(double) + (size_t)kSmNs * sizeof(int);
 
@@ -39,7 +39,7 @@ icp_small_kernel(const IcpParams p) {
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float4 *sxy = reinterpret_cast<float4 *>(smem_raw);             // (-x0, -x1, -y0, -y1) of a target pair
-    float2 *sz = reinterpret_cast<float2 *>(sxy + kSmPairs);        // (-z0, -z1)
+    float4 *sz = reinterpret_cast<float4 *>(sxy + kSmPairs);        // (-z0, -z1, bits: index of target 0, of target 1)
     double *sqx = reinterpret_cast<double *>(sz + kSmPairs);        // float64 targets (n_t <= kSmNt64)
     double *sqy = sqx + kSmNt64;
     double *sqz = sqy + kSmNt64;
@@ -115,12 +115,18 @@ icp_small_kernel(const IcpParams p) {
     // split factor: S lanes share one source point when the tile is narrower than the CTA; the scan
     // reads up to 4 S pairs past the end (software pipelining), which must stay inside the array
     const int npairs = (nt + 1) >> 1;
-    int S = 1;
-    while (S < 32 && ns * (S * 2) <= NT && npairs + 8 * S <= kSmPairs) S *= 2;
-    const int pts_per_round = NT / S;
+    int S0 = 1;
+    while (S0 < 32 && ns * (S0 * 2) <= NT && npairs + 8 * S0 <= kSmPairs) S0 *= 2;
+    const int pts_per_round = NT / S0;
     const int rounds = (ns + pts_per_round - 1) / pts_per_round;
-    const int sub = tid & (S - 1);
-    const int trips2 = ((npairs + S - 1) / S + 1) >> 1;   // scan trips of two pairs per lane
+    // A tile with more points than threads takes several rounds; the last one usually holds only a
+    // few points (n_s = 129: one), which then get as many lanes each as fit instead of a full-length scan.
+    int S_tail = S0;
+    if (p.split_tail && rounds > 1) {
+        const int rem = ns - (rounds - 1) * pts_per_round;
+        S_tail = 1;
+        while (S_tail < 32 && rem * (S_tail * 2) <= NT && npairs + 8 * S_tail <= kSmPairs) S_tail *= 2;
+    }
 
     // float32 copies of the targets, negated (the scan adds), two per entry; the odd tail and the
     // read-ahead padding are points no source can match.  aq = largest coordinate magnitude, scales
@@ -128,7 +134,7 @@ icp_small_kernel(const IcpParams p) {
     float aq = 0.f;
     {
         float amax = 0.f;
-        const int nfill = min(kSmPairs, npairs + 4 * S);
+        const int nfill = min(kSmPairs, npairs + 4 * max(S0, S_tail));
         for (int jj = tid; jj < nfill; jj += NT) {
             const int j0 = 2 * jj, j1 = j0 + 1;
             float ax = 1e18f, ay = 0.f, az = 0.f, bx = 1e18f, by = 0.f, bz = 0.f;
@@ -141,7 +147,7 @@ icp_small_kernel(const IcpParams p) {
                 amax = fmaxf(amax, fmaxf(fabsf(bx), fmaxf(fabsf(by), fabsf(bz))));
             }
             sxy[jj] = make_float4(-ax, -bx, -ay, -by);
-            sz[jj] = make_float2(-az, -bz);
+            sz[jj] = make_float4(-az, -bz, __uint_as_float((uint32_t)j0), __uint_as_float((uint32_t)j1));
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
@@ -165,6 +171,9 @@ icp_small_kernel(const IcpParams p) {
     // ---- phase A: move the points by the current update, find every point's nearest target ----
     auto pass = [&](bool apply) {
         for (int r = 0; r < rounds; ++r) {
+            const int S = r == rounds - 1 ? S_tail : S0;          // lanes per point in this round
+            const int sub = tid & (S - 1);
+            const int trips2 = ((npairs + S - 1) / S + 1) >> 1;   // scan trips of two pairs per lane
             const int i = tid / S + r * pts_per_round;
             const bool active = i < ns;
             double x = 0, y = 0, z = 0;
@@ -190,15 +199,16 @@ icp_small_kernel(const IcpParams p) {
                     // two pairs per trip, the next trip's pairs loaded before this trip's arithmetic
                     // (one warp per scheduler has nothing else to hide the shared-memory latency with)
                     const float2 fx2 = make_float2(fx, fx), fy2 = make_float2(fy, fy), fz2 = make_float2(fz, fz);
-                    auto pair = [&](const float4 qxy, const float2 qz, const uint32_t idx) {
+                    // the target indices ride in the z entry, so a key costs one LOP3 and no index arithmetic
+                    auto pair = [&](const float4 qxy, const float4 qz) {
                         const float2 dx = __fadd2_rn(fx2, make_float2(qxy.x, qxy.y));
                         const float2 dy = __fadd2_rn(fy2, make_float2(qxy.z, qxy.w));
-                        const float2 dz = __fadd2_rn(fz2, qz);
+                        const float2 dz = __fadd2_rn(fz2, make_float2(qz.x, qz.y));
                         float2 d = __fmul2_rn(dx, dx);
                         d = __ffma2_rn(dy, dy, d);
                         d = __ffma2_rn(dz, dz, d);
-                        const uint32_t k0 = (__float_as_uint(d.x) & ~kIdxMask) | idx;
-                        const uint32_t k1 = (__float_as_uint(d.y) & ~kIdxMask) | (idx + 1u);
+                        const uint32_t k0 = (__float_as_uint(d.x) & ~kIdxMask) | __float_as_uint(qz.z);
+                        const uint32_t k1 = (__float_as_uint(d.y) & ~kIdxMask) | __float_as_uint(qz.w);
                         const uint32_t lo = min(k0, k1), hi = max(k0, k1);
                         m2 = __vimin3_u32(m2, hi, max(m1, lo));
                         m1 = min(m1, lo);
@@ -208,20 +218,15 @@ icp_small_kernel(const IcpParams p) {
                         constexpr int SS = decltype(stride_c)::value;
                         const int st = SS ? SS : S;
                         const float4 *pxy = sxy + sub;
-                        const float2 *pz = sz + sub;
-                        uint32_t idx = 2u * (uint32_t)sub;
-                        const uint32_t step = 2u * (uint32_t)st;
                         float4 a0 = pxy[0], a1 = pxy[st];
-                        float2 b0 = pz[0], b1 = pz[st];
+                        float4 b0 = pxy[kSmPairs], b1 = pxy[kSmPairs + st];   // sz = sxy + kSmPairs
 #pragma unroll 2
                         for (int t = 0; t < trips2; ++t) {
                             pxy += 2 * st;
-                            pz += 2 * st;
                             const float4 n0 = pxy[0], n1 = pxy[st];
-                            const float2 c0 = pz[0], c1 = pz[st];
-                            pair(a0, b0, idx);
-                            pair(a1, b1, idx + step);
-                            idx += 2u * step;
+                            const float4 c0 = pxy[kSmPairs], c1 = pxy[kSmPairs + st];
+                            pair(a0, b0);
+                            pair(a1, b1);
                             a0 = n0; a1 = n1; b0 = c0; b1 = c1;
                         }
                     };

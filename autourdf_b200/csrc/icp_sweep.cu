@@ -895,6 +895,14 @@ extern "C" int aurdf_icp_sweep(const void *src_xyz, int pts_dtype, const int32_t
     P.out_rmse = out_rmse; P.out_iters = out_iters; P.out_ntgt = out_ntgt;
     P.dbg_clock = g_dbg_clock;
     P.small_on = small_variant() != 0;
+    {
+        static int split = -1;   // AURDF_ICP_SMALL_SPLIT=0: every round of a tile uses the same lane split (A/B)
+        if (split < 0) {
+            const char *e = getenv("AURDF_ICP_SMALL_SPLIT");
+            split = (e && atoi(e) == 0) ? 0 : 1;
+        }
+        P.split_tail = split;
+    }
     EvPair ev{nullptr, nullptr};
     if (g_prof_on) {
         AURDF_CUDA_CHECK(cudaEventCreate(&ev.a));

@@ -12,10 +12,11 @@ reference's convergence rule.  Synthetic data (autourdf_b200.synth), float64 ari
             between steps); at N GPUs every rank sweeps its own sequences (weak scaling)
             and the fitted poses are all-gathered over NCCL inside the timed region
   e2e       the same through the host-buffer C-ABI call (aurdf_icp_sweep_host): numpy in,
-            numpy out, H2D + D2H copies inside the timed region
-  roofline  the fused per-tile ICP kernel: algorithmic bytes / its measured duration vs the
-            measured HBM peak (MEASURED_PEAKS.json), plus the FP64 issue fraction that
-            actually binds it
+            numpy out, H2D + D2H copies inside the timed region (the call cuts the batch into
+            three frame blocks on separate streams so copies and kernels overlap)
+  roofline  the fused per-tile ICP kernel (icp_small_kernel: every wx200_5 tile is in its class):
+            algorithmic bytes / its measured duration vs the measured HBM peak
+            (MEASURED_PEAKS.json), plus the instruction-issue fraction that actually binds it
   cpu_baseline / --impl reference: the CPU restatement (oracle/, k-d tree NN, OpenMP over
             tiles, all host threads) on the same workload -- the reference's own open3d path
             is not installable here
@@ -53,7 +54,7 @@ def load_peaks():
     return 6650.0, "fallback"
 
 
-def load_traffic(kernel="icp_tiles_kernel"):
+def load_traffic(kernel="icp_small_kernel"):
     """dram__bytes_read.sum + dram__bytes_write.sum of one launch of `kernel`, from the newest
     committed ncu --set full summary (profiles/*_kernels.json, written by profiles/summarize.py)."""
     import glob
@@ -238,11 +239,34 @@ def main():
     gathered = torch.empty((world,) + tuple(plan.out.T.shape), dtype=torch.float64, device=dev) if world > 1 else None
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
 
-    def step():
+    no_gather = os.environ.get("AURDF_BENCH_NO_GATHER") == "1"      # diagnostic only
+
+    def step_eager():
         r = plan.run(d["src"], d["src_off"], d["tgt"], d["tgt_off"], d["tile_frame"], d["box"], d["box_off"], d["init_T"])
-        if world > 1:   # the one exchange step of the path: fitted poses of every rank's sweep
+        if world > 1 and not no_gather:   # the one exchange step of the path: fitted poses of every rank's sweep
             dist.all_gather_into_tensor(gathered, r.T)
         return r
+
+    # N > 1: the step (5 kernels + the NCCL all-gather) is captured once in a CUDA graph, so a step costs
+    # the host one launch instead of ~8 and the ranks do not drift apart on host jitter
+    step, graph = step_eager, None
+    if world > 1 and os.environ.get("AURDF_BENCH_GRAPH", "1") == "1":
+        try:
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(3):
+                    step_eager()
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                step_eager()
+            step = graph.replay
+        except Exception as e:                      # capture not possible here: run eagerly
+            print(f"[bench] CUDA graph capture failed on rank {rank}: {e!r}; running eagerly", file=sys.stderr)
+            step, graph = step_eager, None
+            torch.cuda.synchronize()
 
     def barrier():
         if world > 1:
@@ -258,7 +282,8 @@ def main():
         flush.fill_(i & 0xFF)
         step()
     barrier()
-    L.aurdf_icp_profile_enable(1)
+    if graph is None:
+        L.aurdf_icp_profile_enable(1)
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     for i in range(args.steps):
         flush.fill_(i & 0xFF)        # L2 flush, outside the timed bracket
@@ -266,11 +291,17 @@ def main():
         step()
         ev[i][1].record()
     barrier()
+    dev_ms = sum(a.elapsed_time(b_) for a, b_ in ev)
+    if graph is not None:            # the library's per-launch events cannot live inside a graph: time the
+        L.aurdf_icp_profile_enable(1)  # dominant kernel on a few eager launches after the timed region
+        for i in range(min(args.steps, 20)):
+            flush.fill_(i & 0xFF)
+            plan.run(d["src"], d["src_off"], d["tgt"], d["tgt_off"], d["tile_frame"], d["box"], d["box_off"], d["init_T"])
+        torch.cuda.synchronize()
     L.aurdf_icp_profile_enable(0)
     import ctypes as C
     kms, kn = C.c_double(), C.c_int32()
     L.aurdf_icp_profile_collect(C.byref(kms), C.byref(kn))
-    dev_ms = sum(a.elapsed_time(b_) for a, b_ in ev)
     tmax = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -318,31 +349,36 @@ def main():
         achieved = b_alg / (k_ms * 1e-3) / 1e9
         pairs = float((ns * ntgt * (iters + 1)).sum())             # distance evaluations per launch
         sm_hz = (clocks.get("sm_mhz") or 1965.0) * 1e6
-        # The roof that binds is instruction issue, not HBM: the float32 pre-filter spends ~14.5 issued
-        # instructions per (source, target) pair (6 FP32 + best/second-best tracking, SASS count), exact
-        # float64 work is O(1) per point; peak = 148 SMs x 4 schedulers x 32 lanes per clock.
+        # The roof that binds is instruction issue, not HBM: the float32 pre-filter of icp_small_kernel
+        # issues 18 instructions per PAIR of targets (2 LDS.128, 6 packed f32x2, 2 LOP3, 4 VIMNMX,
+        # 1 VIMNMX3, ~3 loop; SASS count), i.e. 9 per (source, target) evaluation; exact float64 work is
+        # O(1) per point; peak = 148 SMs x 4 schedulers x 32 lanes per clock.
+        instr_per_pair = 9.0
         issue_peak = 148 * 128 * sm_hz
-        issue_rate = 14.5 * pairs / (k_ms * 1e-3)
+        issue_rate = instr_per_pair * pairs / (k_ms * 1e-3)
         traffic, traffic_src = load_traffic()
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                     "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
-                    "kernel": "icp_tiles_kernel", "kernel_ms": k_ms, "kernel_share_of_step": kms.value / dev_ms,
+                    "kernel": "icp_small_kernel", "kernel_ms": k_ms,
+                    "kernel_share_of_step": k_ms / (dev_ms / args.steps),
                     "algorithmic_bytes_per_launch": b_alg,
                     "binding_roof": {"bound": "instruction_issue_and_iteration_latency",
-                                     "pair_evals_per_launch": pairs, "instr_per_pair": 14.5,
+                                     "pair_evals_per_launch": pairs, "instr_per_pair": instr_per_pair,
                                      "achieved_lane_instr_per_s": issue_rate, "peak_lane_instr_per_s": issue_peak,
                                      "frac": issue_rate / issue_peak,
                                      "note": "launch length is set by the slowest tile (max ICP iterations vs mean): "
                                              f"{int(iters.max())} vs {float(iters.mean()):.1f}"}}
-        # ---------------- CPU baseline on this box's host cores ----------------
-        from oracle import icp_oracle as O
-        O.build()
-        modes = cpu_modes(O, b, budget_s=5.0)
-        mode = "reference_serial" if modes["reference_serial"]["value"] >= modes["reference_openmp"]["value"] else "reference_openmp"
-        cpu = {"value": modes[mode]["value"], "unit": UNIT, "cores": modes[mode]["cores"], "kind": "port",
-               "sample": REF_SAMPLE.format(w=WORKLOAD, f=b.n_frames, mode=mode) + "; best of repeated runs",
-               "modes_frames_per_s": {k: m["value"] for k, m in modes.items()},
-               "host_threads": O.lib().orc_max_threads()}
+        # ---------------- CPU baseline on this box's host cores (N = 1 only) ----------------
+        cpu = None
+        if world == 1:
+            from oracle import icp_oracle as O
+            O.build()
+            modes = cpu_modes(O, b, budget_s=5.0)
+            mode = "reference_serial" if modes["reference_serial"]["value"] >= modes["reference_openmp"]["value"] else "reference_openmp"
+            cpu = {"value": modes[mode]["value"], "unit": UNIT, "cores": modes[mode]["cores"], "kind": "port",
+                   "sample": REF_SAMPLE.format(w=WORKLOAD, f=b.n_frames, mode=mode) + "; best of repeated runs",
+                   "modes_frames_per_s": {k: m["value"] for k, m in modes.items()},
+                   "host_threads": O.lib().orc_max_threads()}
         print(json.dumps({
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True,
@@ -351,7 +387,8 @@ def main():
                        "points_per_frame": b.meta["n_points"], "clusters": b.n_clusters,
                        "tiles_per_step_per_gpu": b.n_tiles, "mean_icp_iters": float(iters.mean()),
                        "l2": "flushed between steps (256 MiB write)",
-                       "parallelism": f"tiles sharded by sequence over {world} GPU(s), all-gather of poses"},
+                       "parallelism": f"tiles sharded by sequence over {world} GPU(s), all-gather of poses",
+                       "step_launch": "cuda_graph" if graph is not None else "eager"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": int(L.aurdf_icp_sweep_launches()) * args.steps,
             "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,

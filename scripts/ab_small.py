@@ -31,6 +31,6 @@ for name in sys.argv[1:] or ["wx200_5", "franka", "allegro_hand"]:
     L.aurdf_icp_profile_collect(C.byref(ms), C.byref(n))
     it = r.iters.cpu().numpy()
     same = bool(np.array_equal(it, r0.iters.cpu().numpy()))
-    print(f"SMALL={os.environ.get('AURDF_ICP_SMALL', '1')} MINB={os.environ.get('AURDF_ICP_SMALL_MINB', '5')} {name:13s} tiles {b.n_tiles:5d}  sweep median {np.median(ts)*1e3:8.1f} us"
+    print(f"SMALL={os.environ.get('AURDF_ICP_SMALL', '1')} MINB={os.environ.get('AURDF_ICP_SMALL_MINB', '6')} {name:13s} tiles {b.n_tiles:5d}  sweep median {np.median(ts)*1e3:8.1f} us"
           f"  min {min(ts)*1e3:8.1f} us  icp kernels {ms.value / n.value * 1e3:8.1f} us  iters mean {it.mean():.2f} max {it.max()}  "
           f"frames/s {b.n_frames / (np.median(ts) * 1e-3):9.0f}", flush=True)

@@ -1,0 +1,52 @@
+"""Per-call latency (GPU) of the drop-in ``masked_icp`` on ONE frame transition -- how the reference's
+frame loop calls it (mlp_reg.py:325: K clusters, numpy in / numpy out) -- next to the CPU oracle
+doing the same call.  Writes profiles/<tag>_call_latency.md."""
+import os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np, torch
+from autourdf_b200 import synth
+from autourdf_b200.cluster_icp import masked_icp
+from oracle import icp_oracle as O
+
+tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
+O.build(); O.use_all_host_threads(); O.set_reference_threading(False)
+rows = []
+for name in ("wx200", "wx200_5", "franka", "allegro_hand"):
+    b = synth.make_config(name, n_seq=1, n_frames=4)
+    K = b.n_clusters
+    calls = []
+    for f in range(b.n_frames):
+        tiles = range(f * K, (f + 1) * K)
+        calls.append(([b.src[b.src_off[t]:b.src_off[t + 1]] for t in tiles], [b.box[b.box_off[t]:b.box_off[t + 1]] for t in tiles],
+                      b.tgt[b.tgt_off[f]:b.tgt_off[f + 1]], b.init_T[f * K:(f + 1) * K].astype(np.float32)))
+    for c in calls:
+        masked_icp(*c)                              # warm-up (context, buffers, capacity hints)
+    g, o = [], []
+    for rep in range(10):
+        for c in calls:
+            t0 = time.perf_counter(); w, m = masked_icp(*c); g.append(time.perf_counter() - t0)
+    for rep in range(3):
+        for c in calls:
+            t0 = time.perf_counter(); wo, mo = O.masked_icp(*c); o.append(time.perf_counter() - t0)
+    # parity of every call; tiles whose Kabsch problem is rank-deficient ("Ill-posed tiles") are skipped
+    err, itmax = 0.0, 0
+    for c in calls:
+        dg, do = {}, {}
+        _, m = masked_icp(*c, _details=dg)
+        _, mo = O.masked_icp(*c, _details=do)
+        keep = do["cond"] > 1e-6
+        err = max(err, float(np.abs(m[keep] - mo[keep]).max()))
+        assert np.array_equal(dg["iters"][keep], do["iters"][keep])
+        itmax = max(itmax, int(do["iters"].max()))
+    rows.append((name, K, int(b.tgt_off[1] - b.tgt_off[0]), itmax, 1e6 * np.median(g), 1e6 * np.min(g), 1e6 * np.median(o), np.median(o) / np.median(g), err))
+    print(rows[-1], flush=True)
+with open(os.path.join(ROOT, "profiles", f"{tag}_call_latency.md"), "w") as f:
+    f.write(f"# One `masked_icp` call (one frame transition, K clusters; numpy in, numpy out) as mlp_reg.py:325 issues it ({tag}, 1x B200)\n\n")
+    f.write("Wall-clock of the Python call: list packing, pinned staging, H2D, 5 kernels, D2H, unpacking into K arrays. CPU column: the "
+            "C oracle behind the same signature (`oracle.masked_icp`, k-d tree, tiles one after the other, one thread).\n\n")
+    f.write("A call lasts as long as its slowest cluster: `max ICP iterations` is the largest iteration count any cluster of the timed calls "
+            "needed (open3d's rule has no iteration cap below 10000, so a cluster that keeps oscillating costs the CPU and the GPU alike).\n\n")
+    f.write("| config | K | points/frame | max ICP iterations | GPU call median us | GPU call min us | CPU oracle call median us | CPU / GPU | max pose diff |\n|---|---|---|---|---|---|---|---|---|\n")
+    for r in rows:
+        f.write("| %s | %d | %d | %d | %.0f | %.0f | %.0f | %.1fx | %.1e |\n" % r)

@@ -221,3 +221,60 @@ def test_host_path_frame_blocks_match_device_path(synth):
         assert np.array_equal(o[k], g[k]), f"host path (pinned) differs in {k}"
     h2d, d2h = host.copy_bytes()
     assert h2d > 0 and d2h > 0
+
+
+def test_tile_class_boundaries(oracle):
+    """Tiles at the seams between the small-tile kernel (n_s <= 320, n_t <= 760; float64 targets in
+    shared memory up to 384) and the general kernel, plus the shapes that change the small kernel's
+    lane split (tiny n_s), its padding (odd / even / single targets) and its second round
+    (n_s > 128): every one must give the oracle's correspondences, iteration counts and poses."""
+    import torch
+    from scipy.spatial.transform import Rotation
+    from autourdf_b200 import cluster_icp as ci
+    cases = [(5, 3), (1, 1), (3, 2), (17, 2), (2, 700), (320, 760), (321, 760), (320, 761), (100, 385), (100, 384),
+             (64, 500), (300, 41), (128, 129), (129, 128), (257, 300), (40, 759), (7, 64), (33, 33)]
+    rng = np.random.default_rng(5)
+    srcs, tgts, inits = [], [], []
+    for ns, nt in cases:
+        tgt = rng.uniform(-0.1, 0.1, size=(nt, 3)).astype(np.float32).astype(np.float64)
+        R = Rotation.from_rotvec(rng.normal(scale=0.02, size=3)).as_matrix()
+        pick = tgt[rng.integers(0, nt, size=ns)] + rng.normal(scale=2e-3, size=(ns, 3))
+        srcs.append(((pick - rng.normal(scale=2e-3, size=3)) @ R).astype(np.float32).astype(np.float64))
+        tgts.append(tgt)
+        T0 = np.eye(4)
+        T0[:3, 3] = rng.normal(scale=1e-3, size=3)
+        inits.append(T0)
+    dev = torch.device("cuda")
+
+    def run(idx, max_iter):
+        s_off = np.zeros(len(idx) + 1, np.int32)
+        t_off = np.zeros(len(idx) + 1, np.int32)
+        s_off[1:] = np.cumsum([srcs[i].shape[0] for i in idx])
+        t_off[1:] = np.cumsum([tgts[i].shape[0] for i in idx])
+        t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+        r = ci.icp_sweep(t(np.concatenate([srcs[i] for i in idx])), t(s_off), t(np.concatenate([tgts[i] for i in idx])),
+                         t(t_off), t(np.arange(len(idx), dtype=np.int32)), None, None,
+                         t(np.stack([inits[i] for i in idx])), max_src_per_tile=int(np.diff(s_off).max()),
+                         max_iter=max_iter)
+        torch.cuda.synchronize()
+        return r, s_off
+
+    # the initial correspondence pass of every shape (max_iter = 0: no pose fit, so the 2-3 point
+    # tiles, whose Kabsch problem is rank-deficient, can be compared too)
+    r, s_off = run(list(range(len(cases))), 0)
+    corr, ntg = r.corr.cpu().numpy(), r.ntgt.cpu().numpy()
+    for n, i in enumerate(range(len(cases))):
+        o = oracle.icp_p2p(srcs[i], tgts[i], 1.0, inits[i], max_iter=0)
+        assert ntg[n] == cases[i][1]
+        assert np.array_equal(corr[s_off[n]:s_off[n + 1]], o["corr"]), f"initial pass differs for (n_s, n_t) = {cases[i]}"
+    # full ICP on the well-posed shapes
+    well = [i for i, (ns, nt) in enumerate(cases) if ns >= 7 and nt >= 33]
+    r, s_off = run(well, 40)
+    corr, iters, T = r.corr.cpu().numpy(), r.iters.cpu().numpy(), r.T.cpu().numpy()
+    fit, rmse = r.fitness.cpu().numpy(), r.rmse.cpu().numpy()
+    for n, i in enumerate(well):
+        o = oracle.icp_p2p(srcs[i], tgts[i], 1.0, inits[i], max_iter=40)
+        assert iters[n] == o["iters"], f"iterations differ for {cases[i]}: {iters[n]} vs {o['iters']}"
+        assert np.array_equal(corr[s_off[n]:s_off[n + 1]], o["corr"]), f"correspondences differ for {cases[i]}"
+        assert np.abs(T[n] - o["T"]).max() <= 1e-5
+        assert abs(fit[n] - o["fitness"]) <= 1e-12 and abs(rmse[n] - o["rmse"]) <= 1e-9
