@@ -350,10 +350,10 @@ def main():
         pairs = float((ns * ntgt * (iters + 1)).sum())             # distance evaluations per launch
         sm_hz = (clocks.get("sm_mhz") or 1965.0) * 1e6
         # The roof that binds is instruction issue, not HBM: the float32 pre-filter of icp_small_kernel
-        # issues 18 instructions per PAIR of targets (2 LDS.128, 6 packed f32x2, 2 LOP3, 4 VIMNMX,
-        # 1 VIMNMX3, ~3 loop; SASS count), i.e. 9 per (source, target) evaluation; exact float64 work is
-        # O(1) per point; peak = 148 SMs x 4 schedulers x 32 lanes per clock.
-        instr_per_pair = 9.0
+        # issues 17 instructions per PAIR of targets (2 LDS.128, 6 packed f32x2, 2 LOP3, 4 VIMNMX,
+        # 1 VIMNMX3, ~2 loop; SASS count), i.e. 8.5 per (source, target) evaluation; exact float64 work
+        # is O(1) per point; peak = 148 SMs x 4 schedulers x 32 lanes per clock.
+        instr_per_pair = 8.5
         issue_peak = 148 * 128 * sm_hz
         issue_rate = instr_per_pair * pairs / (k_ms * 1e-3)
         traffic, traffic_src = load_traffic()
