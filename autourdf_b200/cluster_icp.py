@@ -113,18 +113,21 @@ def batch_to_device(batch, device="cuda", pts_dtype=torch.float64):
 
 
 def _pack(arrs, dtype):
+    """list of (n_k,3) arrays -> packed (sum n_k, 3) array of ``dtype`` + CSR offsets (one concatenate:
+    this runs once per call of the drop-in, on the host, inside the caller's frame loop)"""
     off = np.zeros(len(arrs) + 1, dtype=np.int32)
-    if arrs:
-        off[1:] = np.cumsum([a.shape[0] for a in arrs])
-    out = np.empty((int(off[-1]), 3), dtype=dtype)
-    for k, a in enumerate(arrs):
-        out[off[k]:off[k + 1]] = a
+    if not arrs:
+        return np.empty((0, 3), dtype=dtype), off
+    off[1:] = np.cumsum([a.shape[0] for a in arrs])
+    out = np.concatenate(arrs, axis=0, dtype=dtype) if len(arrs) > 1 else np.array(arrs[0], dtype=dtype, order="C")
     return out, off
 
 
 class HostSweep:
-    """Host-buffer path (``aurdf_icp_sweep_host``): numpy in, numpy out.  The context owns a
-    stream, pinned staging and device buffers; one H2D copy, four kernels, one D2H copy."""
+    """Host-buffer path (``aurdf_icp_sweep_host``): numpy in, numpy out.  The context owns streams,
+    pinned staging and device buffers.  A single-frame call with pageable arrays (the reference's
+    frame loop) is one H2D copy, five kernels, one D2H copy; a large frame-major batch is cut into
+    frame blocks on separate streams so copies overlap kernels."""
 
     def __init__(self, device: int | None = None):
         import ctypes as C
@@ -191,8 +194,9 @@ def masked_icp(clusters_local, clusters_world, step_pc_np, matrices, visual=Fals
     ``visual`` / ``colors`` drive open3d GUI calls upstream and are accepted and ignored.
     Returns (list of (n_k,3) float64 world clusters, (K,4,4) float64 poses)."""
     K = min(len(clusters_local), len(clusters_world), len(matrices))   # zip() truncation, :131
-    cl = [np.asarray(c).reshape(-1, 3) for c in clusters_local[:K]]
-    cw = [np.asarray(c).reshape(-1, 3) for c in clusters_world[:K]]
+    as3 = lambda c: c if (type(c) is np.ndarray and c.ndim == 2 and c.shape[1] == 3) else np.asarray(c).reshape(-1, 3)
+    cl = [as3(c) for c in clusters_local[:K]]
+    cw = [as3(c) for c in clusters_world[:K]]
     for c in cw:
         if c.shape[0] == 0:   # np.min on an empty array, :133
             raise ValueError("zero-size array to reduction operation minimum which has no identity")
@@ -204,12 +208,17 @@ def masked_icp(clusters_local, clusters_world, step_pc_np, matrices, visual=Fals
     src, src_off = _pack(cl, np.float64)
     box, box_off = _pack(cw, wdt)
     tgt = np.ascontiguousarray(step_pc_np, dtype=np.float64).reshape(-1, 3)
-    init = np.ascontiguousarray(np.asarray([np.asarray(m, dtype=np.float64) for m in matrices[:K]]).reshape(K, 4, 4))
+    if type(matrices) is np.ndarray and matrices.ndim == 3:
+        init = np.array(matrices[:K], dtype=np.float64, order="C")
+    else:
+        init = np.ascontiguousarray(np.asarray([np.asarray(m, dtype=np.float64) for m in matrices[:K]]).reshape(K, 4, 4))
     r = _host_ctx().run(src, src_off, tgt, np.array([0, tgt.shape[0]], dtype=np.int32), np.zeros(K, dtype=np.int32),
                         box, box_off, init, box_scale=scale, max_corr=th, max_iter=10000, ori_only=ori)
     if _details is not None:
         _details.update(r, src_off=src_off)
-    return [r["world"][src_off[k]:src_off[k + 1]].copy() for k in range(K)], r["T"]
+    # the output buffer is freshly allocated by run(): the per-cluster views own it, no copy needed
+    world, o = r["world"], src_off.tolist()
+    return [world[o[k]:o[k + 1]] for k in range(K)], r["T"]
 
 
 @dataclass

@@ -189,14 +189,21 @@ extern "C" int aurdf_icp_sweep_host(aurdf_ctx *c, const void *src_xyz, int pts_d
     c->last_d2h = 0;
     // host -> device: pinned caller buffers are copied straight from where they are; pageable
     // ones are packed into the context's pinned staging buffer first
+    // One frame block of pageable buffers (the drop-in call of the reference's frame loop): the staging
+    // buffer mirrors the device layout, so everything is packed first and moved by ONE copy each way
+    // instead of eight.
+    const bool one_copy_in = n_chunks == 1 && !is_pinned(src_xyz) && !is_pinned(tgt_xyz) && !is_pinned(box_xyz) &&
+                             !is_pinned(src_off) && !is_pinned(tgt_off) && !is_pinned(tile_frame) &&
+                             !is_pinned(box_off) && !is_pinned(init_T);
     auto h2d = [&](cudaStream_t st, size_t off, const void *base, size_t first, size_t bytes) -> int {
         if (!bytes) return AURDF_OK;
         const char *src = (const char *)base + first;
         const void *from = src;
-        if (!is_pinned(base)) {
+        if (one_copy_in || !is_pinned(base)) {
             memcpy(hi + off + first, src, bytes);
             from = hi + off + first;
         }
+        if (one_copy_in) return AURDF_OK;   // moved by the single copy below
         AURDF_CUDA_CHECK(cudaMemcpyAsync(di + off + first, from, bytes, cudaMemcpyHostToDevice, st));
         c->last_h2d += (int64_t)bytes;
         return AURDF_OK;
@@ -207,6 +214,8 @@ extern "C" int aurdf_icp_sweep_host(aurdf_ctx *c, const void *src_xyz, int pts_d
                    {out_fitness, q_fit, 8, 0, false}, {out_rmse, q_rmse, 8, 0, false},          {out_iters, q_it, 4, 0, false},
                    {out_ntgt, q_nt, 4, 0, false}};
     for (Out &o_ : outs) o_.direct = is_pinned(o_.dst);
+    bool one_copy_out = n_chunks == 1;
+    for (Out &o_ : outs) one_copy_out = one_copy_out && !o_.direct;
 
     struct Chunk { int t0, t1, f0, f1; int64_t s0, s1, cap, cap_upper; size_t ws_off, ws_bytes; };
     Chunk ch[aurdf_ctx::kMaxChunks];
@@ -247,6 +256,10 @@ extern "C" int aurdf_icp_sweep_host(aurdf_ctx *c, const void *src_xyz, int pts_d
             if ((rc2 = h2d(st, o_toff, tgt_off, (size_t)q.f0 * 4, (size_t)(q.f1 - q.f0 + 1) * 4)) != AURDF_OK) return rc2;
             if ((rc2 = h2d(st, o_tf, tile_frame, (size_t)q.t0 * 4, (size_t)nt * 4)) != AURDF_OK) return rc2;
             if ((rc2 = h2d(st, o_init, init_T, (size_t)q.t0 * 16 * 8, (size_t)nt * 16 * 8)) != AURDF_OK) return rc2;
+            if (one_copy_in) {
+                AURDF_CUDA_CHECK(cudaMemcpyAsync(di, hi, in_bytes, cudaMemcpyHostToDevice, st));
+                c->last_h2d += (int64_t)in_bytes;
+            }
         }
         int max_src_c = 0;
         for (int b = q.t0; b < q.t1; ++b) max_src_c = src_off[b + 1] - src_off[b] > max_src_c ? src_off[b + 1] - src_off[b] : max_src_c;
@@ -265,6 +278,11 @@ extern "C" int aurdf_icp_sweep_host(aurdf_ctx *c, const void *src_xyz, int pts_d
         if (rc2 != AURDF_OK) return rc2;
         // optimistic: queue the status and every output behind the kernels; if the capacity guess was
         // too small the chunk is simply run again (inputs already resident)
+        if (one_copy_out) {   // every output section and the status word in one copy
+            AURDF_CUDA_CHECK(cudaMemcpyAsync(ho, d_o, out_bytes, cudaMemcpyDeviceToHost, st));
+            c->last_d2h += (int64_t)out_bytes;
+            return AURDF_OK;
+        }
         AURDF_CUDA_CHECK(cudaMemcpyAsync(ho + q_status + 16 * k, d_o + q_status + 16 * k, 16, cudaMemcpyDeviceToHost, st));
         c->last_d2h += 16;
         for (Out &o_ : outs) {
