@@ -10,7 +10,7 @@ timeout 900 ncu --set full --clock-control none --import-source on -k regex:'icp
     -o gpurun_out/${TAG}_prof python bench.py --steps 3 --warmup 3 > gpurun_out/${TAG}_prof.log 2>&1
 timeout 900 python bench.py 2>&1 | tail -1 | tee gpurun_out/${TAG}_bench.json
 timeout 900 python bench.py --impl reference --steps 20 --warmup 3 2>&1 | tail -1 | tee gpurun_out/${TAG}_bench_reference.json
-timeout 900 python scripts/sweep_configs.py ${TAG} 2>&1 | tail -12
-timeout 600 python scripts/call_latency.py ${TAG} 2>&1 | tail -5
+timeout 900 python tests/measure/sweep_configs.py ${TAG} 2>&1 | tail -12
+timeout 600 python tests/measure/call_latency.py ${TAG} 2>&1 | tail -5
 cp profiles/${TAG}_configs.md profiles/${TAG}_call_latency.md gpurun_out/ 2>/dev/null
 ls -la gpurun_out/

@@ -2,7 +2,7 @@
 a whole run vs (a) the vectorised numpy oracle and (b) the reference's loop structure
 (coord_map.py:253-286: one rotation call per (step, j, k) element) timed on a bounded sample."""
 import os, sys, time
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np, torch

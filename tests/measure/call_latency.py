@@ -2,7 +2,7 @@
 frame loop calls it (mlp_reg.py:325: K clusters, numpy in / numpy out) -- next to the CPU oracle
 doing the same call.  Writes profiles/<tag>_call_latency.md."""
 import os, sys, time
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import numpy as np, torch
 from autourdf_b200 import synth

@@ -1,7 +1,7 @@
 """Throughput + parity table over BASELINE.json's configs (GPU): C1-C4 and points of the C5 sweep.
-Writes profiles/<tag>_configs.md.   python scripts/sweep_configs.py r01"""
+Writes profiles/<tag>_configs.md.   python tests/measure/sweep_configs.py r01"""
 import os, sys, time
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import ctypes as C
 import numpy as np, torch
