@@ -7,7 +7,12 @@ bits with the low 10 bits replaced by the target index; best / second-best key; 
 checks the claim the kernels' bit-exactness rests on -- *whenever the certificate accepts the
 float32 winner, it is the float64 argmin with the reference's operation order*.  The kernels take
 the exact float64 scan for everything the certificate rejects, so a sound certificate is all that
-is needed (autourdf_b200/csrc/icp_small.cu, "float32 pre-filter")."""
+is needed (autourdf_b200/csrc/icp_small.cu, "float32 pre-filter").
+
+Two more emulations guard arithmetic that only runs on the GPU: the lane split / read-ahead index
+arithmetic of icp_small_kernel (every target pair scanned exactly once per point, no shared-memory
+read past the initialised pair array) and its Newton-on-SO(3) pose fit (quaternion accumulation,
+unnormalised update, chord finish, certificate) against umeyama through the C oracle."""
 import numpy as np
 import pytest
 from hypothesis import given, settings, strategies as st
@@ -156,3 +161,126 @@ def test_float32_certificate_is_sound(kind):
     # adversarial sets keep a majority (the rest takes the exact float64 scan in the kernel)
     frac = accepted / checked
     assert frac > (0.995 if kind == "random" else 0.5), f"{kind}: only {frac:.3f} of the points certified"
+
+
+# ------------------------------------------------------------------ lane split / read-ahead arithmetic of icp_small_kernel
+def _lane_split(ns, npairs, NT=128, PAIRS=384):
+    """the integer arithmetic at the top of icp_small_kernel (icp_small.cu: S0, rounds, S_tail, nfill)"""
+    S0 = 1
+    while S0 < 32 and ns * (S0 * 2) <= NT and npairs + 8 * S0 <= PAIRS:
+        S0 *= 2
+    ppr = NT // S0
+    rounds = (ns + ppr - 1) // ppr
+    S_tail = S0
+    if rounds > 1:
+        rem = ns - (rounds - 1) * ppr
+        S_tail = 1
+        while S_tail < 32 and rem * (S_tail * 2) <= NT and npairs + 8 * S_tail <= PAIRS:
+            S_tail *= 2
+    return S0, ppr, rounds, S_tail, min(PAIRS, npairs + 4 * max(S0, S_tail))
+
+
+def test_small_kernel_lane_split_covers_every_pair_and_stays_in_bounds():
+    """every (point, target pair) is scanned exactly once, every lane maps to at most one point per
+    round, and the software-pipelined scan never reads past the initialised part of the pair array"""
+    NT, PAIRS = 128, 384
+    for ns in list(range(1, 140)) + [150, 191, 192, 193, 224, 255, 256, 257, 300, 319, 320]:
+        for nt in (1, 2, 3, 7, 64, 131, 255, 256, 383, 384, 385, 700, 759, 760):
+            npairs = (nt + 1) // 2
+            S0, ppr, rounds, S_tail, nfill = _lane_split(ns, npairs, NT, PAIRS)
+            assert nfill <= PAIRS and rounds * ppr >= ns
+            seen_points = set()
+            for r in range(rounds):
+                S = S_tail if r == rounds - 1 else S0
+                trips2 = ((npairs + S - 1) // S + 1) >> 1
+                pts = {}
+                for tid in range(NT):
+                    i, sub = tid // S + r * ppr, tid & (S - 1)
+                    if i >= ns:
+                        continue
+                    # pairs this lane touches: sub + S * (2 t) and sub + S * (2 t + 1), t < trips2; it also LOADS one trip ahead
+                    touched = [sub + S * k for k in range(2 * trips2)]
+                    assert sub + S * (2 * trips2 + 1) < nfill, (ns, nt, r, S)
+                    pts.setdefault(i, []).extend(touched)
+                for i, tl in pts.items():
+                    real = sorted(j for j in tl if j < npairs)
+                    assert real == list(range(npairs)), (ns, nt, r, i)        # each real pair exactly once
+                    assert i not in seen_points
+                    seen_points.add(i)
+            assert seen_points == set(range(ns))
+
+
+# ------------------------------------------------------------------ the Newton-on-SO(3) pose fit (emulation of kabsch_rotation_newton4)
+def _newton4(sigma):
+    A = sigma.copy()
+    tol = 1e-16 * (abs(A[0, 0]) + abs(A[1, 1]) + abs(A[2, 2]))
+    q = np.array([1.0, 0.0, 0.0, 0.0])
+    vv, conv, steps = 1.0, False, 0
+    adj = hr = None
+    for _ in range(8):
+        k = np.array([A[2, 1] - A[1, 2], A[0, 2] - A[2, 0], A[1, 0] - A[0, 1]])
+        if np.abs(k).max() <= tol:
+            conv = True
+            break
+        if not vv < 1e-10:
+            S = 0.5 * (A + A.T)
+            G = np.trace(S) * np.eye(3) - S
+            det = np.linalg.det(G)
+            adj, hr = np.linalg.inv(G) * det, 0.5 / det
+        v = hr * (adj @ k)
+        vv = float(v @ v)
+        if not vv < 1.0:
+            return None
+        w, x, y, z = q
+        q = np.array([w - (x * v[0] + y * v[1] + z * v[2]), x + (w * v[0] + (y * v[2] - z * v[1])),
+                      y + (w * v[1] + (z * v[0] - x * v[2])), z + (w * v[2] + (x * v[1] - y * v[0]))])
+        steps += 1
+        if vv < 1e-16:
+            conv = True
+            break
+        A = (1.0 - vv) * A + 2.0 * (np.outer(v, v @ A) - np.cross(v, A.T).T)     # (1 + v.v) E^T A, column by column
+        if vv < 1e-13:
+            conv = True
+            break
+    if not conv:
+        return None
+    tr = np.trace(A)
+    e1 = 1e-9 * tr
+    if not (A[0, 0] > e1 and A[0, 0] * A[1, 1] - A[0, 1] * A[1, 0] > e1 * tr and np.linalg.det(A) > e1 * tr * tr):
+        return None
+    w, x, y, z = q
+    s = 2.0 / (q @ q)
+    R = np.array([[1 - s * (y * y + z * z), s * (x * y - z * w), s * (x * z + y * w)],
+                  [s * (x * y + z * w), 1 - s * (x * x + z * z), s * (y * z - x * w)],
+                  [s * (x * z - y * w), s * (y * z + x * w), 1 - s * (x * x + y * y)]])
+    return R, steps
+
+
+def test_newton_pose_fit_equals_umeyama_or_declines(oracle):
+    """the small-tile kernel's rotation fit: whenever it certifies a result, that result is umeyama's
+    U V^T to rounding; reflections and rank-deficient covariances are declined (the kernel then runs
+    the Jacobi SVD)"""
+    rng = np.random.default_rng(11)
+    n_ok = 0
+    for mag in (1.0, 0.3, 1e-1, 1e-2, 1e-3, 1e-5, 1e-8):
+        for _ in range(60):
+            n = int(rng.integers(4, 80))
+            P = rng.normal(size=(n, 3)) * rng.uniform(0.005, 0.1, size=3)
+            Rt = Rotation.from_rotvec(rng.normal(size=3) / np.sqrt(3) * mag).as_matrix()
+            Q = P @ Rt.T + rng.normal(scale=5e-4, size=P.shape)
+            sigma = (Q - Q.mean(0)).T @ (P - P.mean(0)) / n
+            ref = oracle.kabsch(P, Q, np.arange(n, dtype=np.int32))[:3, :3]
+            r = _newton4(sigma)
+            if r is None:
+                assert mag >= 0.3          # only large rotations may be handed to the fallback
+                continue
+            R, steps = r
+            n_ok += 1
+            assert np.abs(R - ref).max() <= 1e-12 and np.abs(R @ R.T - np.eye(3)).max() <= 1e-14
+            if mag <= 1e-3:
+                assert steps <= 3          # late ICP iterations: one full step + a short finish (or two)
+    assert n_ok > 300
+    mirror = np.diag([1.0, 1.0, -1.0]) * 1e-4                      # det < 0: umeyama flips an axis; Newton must decline
+    assert _newton4(mirror) is None
+    rank1 = np.outer([1.0, 2.0, 3.0], [0.5, -1.0, 2.0]) * 1e-5     # collinear matches
+    assert _newton4(rank1) is None
