@@ -43,7 +43,7 @@ class IcpResult:
 
 class IcpSweep:
     """Reusable plan: owns outputs + workspace for a fixed problem shape, launches without
-    any host synchronisation (all four kernels go to the current stream)."""
+    any host synchronisation (all five kernels go to the current stream)."""
 
     def __init__(self, n_tiles: int, total_src: int, tgt_capacity: int, max_src_per_tile: int = 0, device=None):
         self.lib = _lib.lib()

@@ -94,17 +94,21 @@ AURDF_API int aurdf_icp_sweep(const void *src_xyz, int pts_dtype, const int32_t 
 /* Number of kernels one aurdf_icp_sweep() call launches (for launch accounting). */
 AURDF_API int aurdf_icp_sweep_launches(void);
 
-/* Live timing of the dominant kernel (the fused per-tile ICP kernel): while enabled, every
- * aurdf_icp_sweep() on this thread brackets that kernel with CUDA events on the caller's
- * stream; collect() waits for them, returns the summed duration and launch count, and resets. */
+/* Live timing of the dominant kernel (the fused per-tile ICP: icp_small_kernel for tiles of up to
+ * 320 source / 760 target points plus icp_tiles_kernel for the rest): while enabled, every
+ * aurdf_icp_sweep() on this thread brackets those two launches with CUDA events on the caller's
+ * stream; collect() waits for them, returns the summed duration and launch count, and resets.
+ * Do not enable it while the stream is being captured into a CUDA graph. */
 AURDF_API int aurdf_icp_profile_enable(int on);
 AURDF_API int aurdf_icp_profile_collect(double *total_ms, int32_t *n_launches);
 
 /* ---------------------------------------------------------------------------------------
- * Host-buffer path: same operator with HOST pointers.  A context owns a stream, pinned
+ * Host-buffer path: same operator with HOST pointers.  A context owns streams, pinned
  * staging and growable device buffers; the call copies inputs host->device, runs the sweep,
  * copies results device->host and returns when they are in place.  This is what a
- * reference-side binding calls from the numpy world of mlp_reg.py:325.
+ * reference-side binding calls from the numpy world of mlp_reg.py:325.  A large batch whose
+ * tile_frame is non-decreasing is cut into frame blocks on separate streams so that copies
+ * overlap kernels; a single-frame call with pageable buffers is one copy each way.
  * ------------------------------------------------------------------------------------- */
 typedef struct aurdf_ctx aurdf_ctx;
 
