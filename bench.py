@@ -370,7 +370,7 @@ def main():
                                              f"{int(iters.max())} vs {float(iters.mean()):.1f}"}}
         # ---------------- CPU baseline on this box's host cores (N = 1 only) ----------------
         cpu = None
-        if world == 1:
+        if world == 1 and os.environ.get("AURDF_BENCH_SKIP_CPU") != "1":   # (the skip is for quick A/B runs only)
             from oracle import icp_oracle as O
             O.build()
             modes = cpu_modes(O, b, budget_s=5.0)
