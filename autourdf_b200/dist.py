@@ -1,5 +1,8 @@
 """Multi-GPU layer of the cluster-ICP sweep: one process per GPU (torch.distributed), tiles
-sharded by contiguous frame blocks, ONE all-gather of the fitted poses per sweep.
+sharded by contiguous frame blocks (batch mode: every target cloud lives on exactly one GPU) or by
+contiguous tile ranges (real-pipeline mode: the K clusters of the current frame transition are
+split over the GPUs, each holding a replica of the frame's cloud), ONE all-gather of the fitted
+poses per sweep.
 
 Why it shards: the K cluster tiles of a frame are independent (the loop at reference
 PointCloud/cluster_icp.py:131 carries no state) and so are frames once their init poses are
@@ -38,22 +41,48 @@ def frame_partition(batch, world: int):
     return [(cuts[r], cuts[r + 1]) for r in range(world)]
 
 
-def sharded_sweep(batch, run_local, group=None, device="cpu"):
+def tile_partition(batch, world: int):
+    """Contiguous tile ranges [b0, b1) per rank, balanced by the pair-evaluation estimate n_s * M of
+    each tile.  Frames may be split between ranks (their clouds are then replicated): this is how one
+    sweep of K clusters (real-pipeline mode) spreads over the GPUs."""
+    B = batch.n_tiles
+    ns = np.diff(batch.src_off).astype(np.float64)
+    M = np.diff(batch.tgt_off).astype(np.float64)
+    cost = ns * M[batch.tile_frame] if B else np.zeros(0)
+    cum = np.concatenate([[0.0], np.cumsum(cost)])
+    cuts = [0]
+    for r in range(1, world):
+        b = int(np.searchsorted(cum, cum[-1] * r / world, side="left"))
+        cuts.append(min(max(b, cuts[-1]), B))
+    cuts.append(B)
+    return [(cuts[r], cuts[r + 1]) for r in range(world)]
+
+
+def sharded_sweep(batch, run_local, group=None, device="cpu", by="frames"):
     """Run ``run_local(sub_batch) -> dict(T (b,4,4), fitness, rmse, iters)`` on this rank's
-    frame block and all-gather the per-tile results.  Returns (gathered dict over ALL tiles in
-    the original tile order, this rank's local result dict, (f0, f1))."""
+    share and all-gather the per-tile results.  ``by="frames"``: contiguous frame blocks;
+    ``by="tiles"``: contiguous tile ranges with replicated target clouds (a single frame's K
+    clusters over several GPUs).  Returns (gathered dict over ALL tiles in the original tile
+    order, this rank's local result dict, this rank's (f0, f1) or (b0, b1))."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
-    parts = frame_partition(batch, world)
-    f0, f1 = parts[rank]
-    sub = batch.frame_slice(f0, f1)
+    assert by in ("frames", "tiles")
+    if by == "tiles":
+        parts = tile_partition(batch, world)
+        f0, f1 = parts[rank]
+        sub = batch.tile_slice(f0, f1)
+        counts = [b - a for a, b in parts]
+    else:
+        parts = frame_partition(batch, world)
+        f0, f1 = parts[rank]
+        sub = batch.frame_slice(f0, f1)
+        # tiles per rank (frame-major tile order => each rank owns a contiguous tile range)
+        counts = [int(((batch.tile_frame >= a) & (batch.tile_frame < b)).sum()) for a, b in parts]
     local = run_local(sub) if sub.n_tiles else dict(T=np.zeros((0, 4, 4)), fitness=np.zeros(0), rmse=np.zeros(0),
                                                     iters=np.zeros(0, dtype=np.int32))
     if world == 1:
         return dict(T=np.asarray(local["T"]), fitness=np.asarray(local["fitness"]), rmse=np.asarray(local["rmse"]),
                     iters=np.asarray(local["iters"])), local, (f0, f1)
-    # tiles per rank (frame-major tile order => each rank owns a contiguous tile range)
-    counts = [int(((batch.tile_frame >= a) & (batch.tile_frame < b)).sum()) for a, b in parts]
     width = max(max(counts), 1)
     # one padded (width, 19) float64 payload per rank: 16 pose entries + fitness + rmse + iters
     pay = torch.zeros((width, 19), dtype=torch.float64, device=device)

@@ -171,6 +171,27 @@ class SweepBatch:
                           dict(self.meta))
 
 
+    def tile_slice(self, b0, b1):
+        """sub-batch holding tiles [b0, b1) and (a copy of) every frame they refer to: the unit of
+        cluster-level sharding, where each GPU holds a replica of the frame's target cloud"""
+        b0, b1 = int(b0), int(b1)
+        if b1 <= b0:
+            z = np.zeros(1, dtype=np.int32)
+            return SweepBatch(self.src[:0], z, self.tgt[:0], z, self.tile_frame[:0], self.box[:0], z.copy(),
+                              self.init_T[:0], 0, self.n_clusters, dict(self.meta))
+        frames = np.unique(self.tile_frame[b0:b1])                      # sorted
+        remap = np.full(int(self.tgt_off.shape[0]) - 1, -1, dtype=np.int32)
+        remap[frames] = np.arange(frames.size, dtype=np.int32)
+        tgt = np.concatenate([self.tgt[self.tgt_off[f]:self.tgt_off[f + 1]] for f in frames])
+        tgt_off = np.zeros(frames.size + 1, dtype=np.int32)
+        tgt_off[1:] = np.cumsum([self.tgt_off[f + 1] - self.tgt_off[f] for f in frames])
+        s0, s1 = int(self.src_off[b0]), int(self.src_off[b1])
+        x0, x1 = int(self.box_off[b0]), int(self.box_off[b1])
+        return SweepBatch(self.src[s0:s1], self.src_off[b0:b1 + 1] - s0, tgt, tgt_off, remap[self.tile_frame[b0:b1]],
+                          self.box[x0:x1], self.box_off[b0:b1 + 1] - x0, self.init_T[b0:b1], int(frames.size),
+                          self.n_clusters, dict(self.meta))
+
+
 def kmeans_frame0(pts, k, seed):
     """cluster_icp.py:67 -- sklearn k_means(init='k-means++'); returns labels"""
     from sklearn.cluster import k_means

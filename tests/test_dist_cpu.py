@@ -33,6 +33,15 @@ def _worker(rank, world, port, q):
         ok = (np.array_equal(allr["T"], full["T"]) and np.array_equal(allr["iters"], full["iters"])
               and np.array_equal(allr["rmse"], full["rmse"]) and np.array_equal(allr["fitness"], full["fitness"]))
         parts = frame_partition(b, world)
+        # real-pipeline mode: ONE frame transition, its K clusters split over the ranks, the
+        # frame's cloud replicated; and the same split over the whole batch
+        one = b.frame_slice(2, 3)
+        allt, loct, (b0, b1) = sharded_sweep(one, run_local, device="cpu", by="tiles")
+        full1 = run_local(one)
+        ok = ok and np.array_equal(allt["T"], full1["T"]) and np.array_equal(allt["iters"], full1["iters"])
+        ok = ok and loct["T"].shape[0] == b1 - b0 and 0 < b1 - b0 < one.n_tiles
+        allb, _, _ = sharded_sweep(b, run_local, device="cpu", by="tiles")
+        ok = ok and np.array_equal(allb["T"], full["T"]) and np.array_equal(allb["fitness"], full["fitness"])
         q.put((rank, ok, (f0, f1), parts, int(local["T"].shape[0])))
     except Exception as e:  # surface the failure instead of letting the parent wait for the queue
         q.put((rank, False, repr(e), None, 0))
@@ -59,6 +68,36 @@ def test_sharded_sweep_equals_single_process_gloo():
     assert parts[0][0] == 0 and parts[-1][1] == 5 and parts[0][1] == parts[1][0]     # contiguous cover of 5 frames
     assert [r[2] for r in res] == parts
     assert sum(r[4] for r in res) == 50                                                # 5 frames x 10 clusters
+
+
+def test_tile_partition_and_tile_slice():
+    """cluster-level sharding: contiguous balanced tile ranges; a tile slice carries exactly the frames its
+    tiles refer to, re-indexed, and sweeping the slices reproduces the sweep of the whole batch"""
+    sys.path.insert(0, ROOT)
+    from autourdf_b200 import synth
+    from autourdf_b200.dist import tile_partition
+    from oracle import icp_oracle as O
+    O.build()
+    b = synth.make_config("wx200", n_frames=4)
+    run = lambda s: O.masked_icp_sweep(s.src, s.src_off, s.tgt, s.tgt_off, s.tile_frame, s.box, s.box_off, s.init_T, nthreads=1)
+    full = run(b)
+    for world in (1, 2, 3, 7, 40):
+        parts = tile_partition(b, world)
+        assert len(parts) == world and parts[0][0] == 0 and parts[-1][1] == b.n_tiles
+        assert all(parts[i][1] == parts[i + 1][0] for i in range(world - 1))
+        pieces = []
+        for a, c in parts:
+            sub = b.tile_slice(a, c)
+            assert sub.n_tiles == c - a and sub.tgt_off.shape[0] == sub.n_frames + 1
+            if c > a:
+                assert sub.tile_frame.min() == 0 and sub.tile_frame.max() == sub.n_frames - 1
+                assert sub.n_frames == np.unique(b.tile_frame[a:c]).size
+                pieces.append(run(sub))
+        assert np.array_equal(np.concatenate([p["T"] for p in pieces]), full["T"])
+        assert np.array_equal(np.concatenate([p["corr"] for p in pieces]), full["corr"])
+    one = b.frame_slice(1, 2)
+    sizes = [c - a for a, c in tile_partition(one, 4)]
+    assert sum(sizes) == one.n_tiles and max(sizes) - min(sizes) <= 2
 
 
 def test_frame_partition_properties():
