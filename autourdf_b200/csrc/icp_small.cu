@@ -1,20 +1,24 @@
 // icp_small.cu -- the per-tile ICP of icp_sweep.cu, re-cut for the tiles of the named configs
-// (n_s <= 320 source points, n_t <= 768 masked targets: wx200 / franka / allegro_hand).
+// (n_s <= 320 source points, n_t <= 760 masked targets: wx200 / franka / allegro_hand).
 //
 // Why a second kernel.  One launch of the sweep is bounded by the iteration latency of its slowest
 // tile (68 ICP iterations against a mean of 14 on wx200_5), not by issue or memory throughput, and
 // that tile used to start only in the third wave of CTAs.  This kernel therefore
-//   * keeps a tile's whole state in < 30 KB of shared memory and <= 72 registers, so 7 CTAs of
-//     128 threads are resident per SM: all 900 tiles of wx200_5 start at t = 0;
+//   * keeps a tile's whole state in 34 KB of shared memory and <= 80 registers, so 6 CTAs of
+//     128 threads are resident per SM: (almost) all 900 tiles of wx200_5 start at t = 0;
 //   * scans targets two at a time with packed float32 arithmetic (add/mul/fma.f32x2) and tracks
-//     best / second-best as one 32-bit key per target (distance bits | index), 5 integer
-//     min/max per pair instead of compare+select chains;
-//   * replaces the per-lane 16-accumulator moment sums and the transposing shuffle reduction by a
-//     shared-memory reduction with one thread group per moment;
-//   * fits the pose with the shortened Newton-on-SO(3) iteration (kabsch_rotation_newton4).
+//     best / second-best as one 32-bit key per target (distance bits | index): 5 integer min/max
+//     and 2 logic operations per pair of targets instead of compare+select chains; the loop is
+//     software pipelined and specialised on the lane stride;
+//   * sums the 16 moments + sum d^2 of the Kabsch fit as one small matrix product on the FP64
+//     tensor cores (mma.m8n8k4.f64) instead of per-lane accumulators and a shuffle reduction;
+//   * fits the pose with a short Newton-on-SO(3) iteration (kabsch_rotation_newton4);
+//   * keeps ONE copy of every phase in the iteration loop: the loop body is 22 KB of code instead
+//     of 107 KB, which matters for a single warp re-fetching it every iteration.
 // Semantics are those of icp_tiles_kernel (open3d RegistrationICP point-to-point inside
 // masked_icp, cluster_icp.py:118-191): the argmin is certified against float64 or re-done in
 // float64 with the reference's operation order, so correspondences stay bit-identical.
+// Measurements behind each choice: profiles/r01_notes.md.
 #include <math.h>
 #include <stdlib.h>
 
