@@ -19,6 +19,6 @@ ci.masked_icp([b.src[b.src_off[t]:b.src_off[t + 1]] for t in range(K)], [b.box[b
               b.tgt[b.tgt_off[0]:b.tgt_off[1]], b.init_T[:K].astype(np.float32))
 print("iters", r.iters.cpu().numpy()[:10])
 PY
-timeout 900 compute-sanitizer --tool "$TOOL" --kernel-regex kns=aurdf --log-file gpurun_out/sanitize_$TOOL.log \
+timeout ${SAN_TIMEOUT:-900} compute-sanitizer --tool "$TOOL" --log-file gpurun_out/sanitize_$TOOL.log \
     python /tmp/aurdf_sanitize_target.py
 tail -5 gpurun_out/sanitize_$TOOL.log
