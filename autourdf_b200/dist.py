@@ -21,9 +21,23 @@ import torch
 import torch.distributed as dist
 
 
+def _to_np(a):
+    """numpy view/copy of a numpy array or a (possibly CUDA) torch tensor"""
+    return a.detach().cpu().numpy() if torch.is_tensor(a) else np.asarray(a)
+
+
+def _require_frame_major(batch):
+    """frame blocks are contiguous tile ranges only if tiles are sorted by frame (every producer in this
+    package emits them that way); anything else must shard by="tiles" """
+    if batch.n_tiles > 1 and not np.all(np.diff(batch.tile_frame) >= 0):
+        raise ValueError("sharding by frames needs frame-major tiles (tile_frame non-decreasing); "
+                         "use by='tiles' for an unsorted batch")
+
+
 def frame_partition(batch, world: int):
     """Contiguous frame ranges [f0, f1) per rank, balanced by the pair-evaluation estimate
     sum(n_s * M) of each frame (keeps every target cloud on exactly one GPU)."""
+    _require_frame_major(batch)
     F = batch.n_frames
     ns = np.diff(batch.src_off).astype(np.float64)
     M = np.diff(batch.tgt_off).astype(np.float64)
@@ -81,8 +95,8 @@ def sharded_sweep(batch, run_local, group=None, device="cpu", by="frames"):
     local = run_local(sub) if sub.n_tiles else dict(T=np.zeros((0, 4, 4)), fitness=np.zeros(0), rmse=np.zeros(0),
                                                     iters=np.zeros(0, dtype=np.int32))
     if world == 1:
-        return dict(T=np.asarray(local["T"]), fitness=np.asarray(local["fitness"]), rmse=np.asarray(local["rmse"]),
-                    iters=np.asarray(local["iters"])), local, (f0, f1)
+        return dict(T=_to_np(local["T"]), fitness=_to_np(local["fitness"]), rmse=_to_np(local["rmse"]),
+                    iters=_to_np(local["iters"])), local, (f0, f1)
     width = max(max(counts), 1)
     # one padded (width, 19) float64 payload per rank: 16 pose entries + fitness + rmse + iters
     pay = torch.zeros((width, 19), dtype=torch.float64, device=device)
@@ -112,3 +126,61 @@ def cuda_run_local(device=None, **kw):
         return dict(T=r.T, fitness=r.fitness, rmse=r.rmse, iters=r.iters, corr=r.corr, world=r.world, ntgt=r.ntgt)
 
     return run
+
+
+class ShardedSweep:
+    """Device-resident sharding of ONE batch over the ranks of ``group`` (strong scaling: the total work
+    is fixed, every rank owns a contiguous frame block or tile range).  The partition, the upload of this
+    rank's share and the plan (outputs + workspace) happen once; ``run()`` is then this rank's five kernel
+    launches plus ONE ``all_gather_into_tensor`` of the fitted poses (tiles x 16 float64, padded to the
+    widest share), all on the current stream with no host synchronisation.  Reference: the per-cluster
+    loop at PointCloud/cluster_icp.py:131 carries no state between clusters, mlp_reg.py:434-435 none
+    between sequences."""
+
+    def __init__(self, batch, device, group=None, by="frames", **sweep_kw):
+        from . import cluster_icp as ci
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.group, self.kw = group, sweep_kw
+        assert by in ("frames", "tiles")
+        if by == "tiles":
+            self.parts = tile_partition(batch, self.world)
+            lo, hi = self.parts[self.rank]
+            self.sub = batch.tile_slice(lo, hi)
+            self.counts = [b - a for a, b in self.parts]
+        else:
+            self.parts = frame_partition(batch, self.world)
+            lo, hi = self.parts[self.rank]
+            self.sub = batch.frame_slice(lo, hi)
+            self.counts = [int(((batch.tile_frame >= a) & (batch.tile_frame < b)).sum()) for a, b in self.parts]
+        self.width = max(max(self.counts), 1)
+        n = self.sub.n_tiles
+        assert n == self.counts[self.rank]
+        dev = torch.device(device)
+        self.pay = torch.zeros((self.width, 16), dtype=torch.float64, device=dev)
+        self.gathered = torch.empty((self.world * self.width, 16), dtype=torch.float64, device=dev)
+        self.plan, self.d = None, None
+        if n:
+            self.d = ci.batch_to_device(self.sub, device=dev)
+            max_src = int(np.diff(self.sub.src_off).max())
+            r0 = ci.icp_sweep(self.d["src"], self.d["src_off"], self.d["tgt"], self.d["tgt_off"], self.d["tile_frame"],
+                              self.d["box"], self.d["box_off"], self.d["init_T"], max_src_per_tile=max_src, **sweep_kw)
+            self.plan = ci.IcpSweep(n, self.sub.src.shape[0], r0.needed_capacity() + 64, max_src, device=dev)
+            self.plan.out.T = self.pay[:n].view(n, 4, 4)      # poses land in the all-gather payload directly
+
+    def run(self):
+        """one sharded sweep; returns the gathered (world * width, 16) pose buffer (device)"""
+        if self.plan is not None:
+            d = self.d
+            self.plan.run(d["src"], d["src_off"], d["tgt"], d["tgt_off"], d["tile_frame"], d["box"], d["box_off"],
+                          d["init_T"], **self.kw)
+        if self.world > 1:
+            dist.all_gather_into_tensor(self.gathered, self.pay, group=self.group)
+        else:
+            self.gathered.copy_(self.pay)
+        return self.gathered
+
+    def poses(self):
+        """(B,4,4) float64 numpy: the gathered poses in the original tile order"""
+        g = self.gathered.cpu().numpy().reshape(self.world, self.width, 16)
+        return np.concatenate([g[r, :self.counts[r]] for r in range(self.world)], axis=0).reshape(-1, 4, 4)

@@ -2,6 +2,7 @@
 """bench.py -- cluster-ICP frames/s on B200 (BASELINE.json metric), one JSON line on stdout.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+                    [--scaling weak|strong] [--workload wx200_5|franka|allegro_hand|c5:<pts>x<clusters>]
 
 A "step" is one pass of the hot path over the wx200_5 workload (C2: 5 sequences x 10 frames
 = 45 frame transitions, 2048 points/frame, 20 clusters -> 900 (frame, cluster) tiles); one
@@ -33,8 +34,8 @@ import time
 
 import numpy as np
 
-# one JSON line on stdout: keep NCCL's version banner out of it
-os.environ["NCCL_DEBUG"] = os.environ.get("AURDF_NCCL_DEBUG", "WARN")
+# NCCL_DEBUG is the caller's to set (the driver reads NCCL's own log for the rank count); the JSON
+# line is the LAST line this process prints on stdout.
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
@@ -114,10 +115,41 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def make_workload(rank=0):
+def make_workload(rank=0, name=None):
+    """the synthetic batch of a named BASELINE.json config, or of a C5 sweep point "c5:<points>x<clusters>[x<frames>]"
+    (one sequence of <frames> transitions + 1 frames; default 10 transitions)"""
     from autourdf_b200 import synth
-    cfg = dict(synth.CONFIGS[WORKLOAD])
+    name = name or WORKLOAD
+    if name.startswith("c5:"):
+        dims = [int(x) for x in name[3:].split("x")]
+        n_pts, n_cl = dims[0], dims[1]
+        n_tr = dims[2] if len(dims) > 2 else 10
+        return synth.make_batch(n_points=n_pts, n_clusters=n_cl, n_seq=1, n_frames=n_tr + 1, dof=5, cid=5,
+                                seed=5000 + 17 * rank)
+    cfg = dict(synth.CONFIGS[name])
     return synth.make_batch(**cfg, seed=cfg["cid"] * 1000 + 17 * rank)
+
+
+def config_dict(b, name, scaling, world):
+    """identical in both arms (the driver compares them)"""
+    per = "" if scaling == "strong" else "_per_gpu"
+    return {"workload": name, "frames_per_step" + per: b.n_frames, "points_per_frame": b.meta["n_points"],
+            "clusters": b.n_clusters, "tiles_per_step" + per: b.n_tiles,
+            "l2": "flushed between steps (256 MiB write) on the GPU arm",
+            "parallelism": (f"one {name} batch sharded by frame blocks over {world} GPU(s)" if scaling == "strong" else
+                            f"every GPU sweeps its own {name} sequences ({world} GPU(s))") + ", one all-gather of poses"}
+
+
+def finish(world):
+    """bounded exit: the JSON line is out; tear the process group down under a watchdog and leave"""
+    sys.stdout.flush()
+    sys.stderr.flush()
+    if world > 1:
+        import torch.distributed as dist
+        t = threading.Thread(target=dist.destroy_process_group, daemon=True)
+        t.start()
+        t.join(20.0)
+    os._exit(0)
 
 
 def cpu_sweep(O, b, nthreads=0):
@@ -169,9 +201,10 @@ def run_reference(args):
     structure (see cpu_modes).  Rank 0 only."""
     if int(os.environ.get("RANK", "0")) != 0:
         return
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     from oracle import icp_oracle as O
     O.build()
-    b = make_workload(0)
+    b = make_workload(0, args.workload)
     modes = cpu_modes(O, b, budget_s=2.0)
     mode = "reference_serial" if modes["reference_serial"]["value"] >= modes["reference_openmp"]["value"] else "reference_openmp"
     inner = mode == "reference_openmp"
@@ -187,16 +220,16 @@ def run_reference(args):
     v = b.n_frames * args.steps / dt
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": args.scaling,
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "frames_per_step": b.n_frames, "points_per_frame": b.meta["n_points"],
-                   "clusters": b.n_clusters, "tiles_per_step": b.n_tiles},
+        "config": config_dict(b, args.workload, args.scaling, world),
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": modes[mode]["cores"], "kind": "port",
-                         "sample": REF_SAMPLE.format(w=WORKLOAD, f=b.n_frames, mode=mode),
+                         "sample": REF_SAMPLE.format(w=args.workload, f=b.n_frames, mode=mode),
                          "modes_frames_per_s": {k: m["value"] for k, m in modes.items()},
+                         "all_core_port_frames_per_s": modes["tile_parallel"]["value"],
                          "host_threads": O.lib().orc_max_threads()},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }))
+    }), flush=True)
 
 
 def main():
@@ -205,10 +238,16 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak (default, the driver's contract): every GPU sweeps its own sequences; strong: ONE "
+                         "batch of --workload sharded over the GPUs by frame blocks (autourdf_b200.dist.ShardedSweep)")
+    ap.add_argument("--workload", default=WORKLOAD)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
         return run_reference(args)
+
+    import ctypes as C
 
     import torch
     import torch.distributed as dist
@@ -224,33 +263,66 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     L = _lib.lib()
+    strong = args.scaling == "strong"
 
-    b = make_workload(rank)
-    d = ci.batch_to_device(b, device=dev)
-    max_src = int(np.diff(b.src_off).max())
-    r0 = ci.icp_sweep(d["src"], d["src_off"], d["tgt"], d["tgt_off"], d["tile_frame"], d["box"], d["box_off"],
-                      d["init_T"], max_src_per_tile=max_src)
-    torch.cuda.synchronize()
-    need = r0.needed_capacity()
-    ntgt = r0.ntgt.cpu().numpy().astype(np.int64)
-    iters = r0.iters.cpu().numpy().astype(np.int64)
-    ns = np.diff(b.src_off).astype(np.int64)
-    plan = ci.IcpSweep(b.n_tiles, b.src.shape[0], need + 64, max_src, device=dev)
-    gathered = torch.empty((world,) + tuple(plan.out.T.shape), dtype=torch.float64, device=dev) if world > 1 else None
+    # weak: this rank's own sequences; strong: the same batch on every rank, of which it keeps its share
+    b_all = make_workload(0 if strong else rank, args.workload)
+    sharded = None
+    if strong:
+        from autourdf_b200.dist import ShardedSweep
+        sharded = ShardedSweep(b_all, dev)
+        b = sharded.sub
+    else:
+        b = b_all
+    have = b.n_tiles > 0
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
+    ns = np.diff(b.src_off).astype(np.int64)
+    if strong:
+        plan, d = sharded.plan, sharded.d
+        r0 = plan.out if have else None
+        gathered = None
+    else:
+        d = ci.batch_to_device(b, device=dev)
+        max_src = int(ns.max())
+        r0 = ci.icp_sweep(d["src"], d["src_off"], d["tgt"], d["tgt_off"], d["tile_frame"], d["box"], d["box_off"],
+                          d["init_T"], max_src_per_tile=max_src)
+        torch.cuda.synchronize()
+        plan = ci.IcpSweep(b.n_tiles, b.src.shape[0], r0.needed_capacity() + 64, max_src, device=dev)
+        gathered = torch.empty((world,) + tuple(plan.out.T.shape), dtype=torch.float64, device=dev) if world > 1 else None
+    if strong:
+        sharded.run()
+    torch.cuda.synchronize()
+    ntgt = r0.ntgt.cpu().numpy().astype(np.int64) if have else np.zeros(0, np.int64)
+    iters = r0.iters.cpu().numpy().astype(np.int64) if have else np.zeros(0, np.int64)
+
+    check = None
+    if strong:
+        # the gathered poses of the sharded sweep must be bit-identical to ONE GPU's sweep of the
+        # whole batch (rank 0 runs it once, outside the timed region)
+        if rank == 0:
+            dall = ci.batch_to_device(b_all, device=dev)
+            rf = ci.icp_sweep(dall["src"], dall["src_off"], dall["tgt"], dall["tgt_off"], dall["tile_frame"], dall["box"],
+                              dall["box_off"], dall["init_T"], max_src_per_tile=int(np.diff(b_all.src_off).max()))
+            torch.cuda.synchronize()
+            check = bool(np.array_equal(sharded.poses(), rf.T.cpu().numpy()))
+            assert check, "sharded sweep differs from the single-GPU sweep"
+            del dall, rf
 
     no_gather = os.environ.get("AURDF_BENCH_NO_GATHER") == "1"      # diagnostic only
 
     def step_eager():
+        if strong:
+            return sharded.run()
         r = plan.run(d["src"], d["src_off"], d["tgt"], d["tgt_off"], d["tile_frame"], d["box"], d["box_off"], d["init_T"])
         if world > 1 and not no_gather:   # the one exchange step of the path: fitted poses of every rank's sweep
             dist.all_gather_into_tensor(gathered, r.T)
         return r
 
-    # N > 1: the step (5 kernels + the NCCL all-gather) is captured once in a CUDA graph, so a step costs
-    # the host one launch instead of ~8 and the ranks do not drift apart on host jitter
+    # Optional (AURDF_BENCH_GRAPH=1): the step (kernels + the NCCL all-gather) captured once in a CUDA graph.
+    # Off by default: it bought 2 % at 4 GPUs and a live graph holding NCCL work must be destroyed before the
+    # process group is.
     step, graph = step_eager, None
-    if world > 1 and os.environ.get("AURDF_BENCH_GRAPH", "1") == "1":
+    if world > 1 and os.environ.get("AURDF_BENCH_GRAPH", "0") == "1":
         try:
             side = torch.cuda.Stream(device=dev)
             side.wait_stream(torch.cuda.current_stream())
@@ -296,17 +368,23 @@ def main():
         L.aurdf_icp_profile_enable(1)  # dominant kernel on a few eager launches after the timed region
         for i in range(min(args.steps, 20)):
             flush.fill_(i & 0xFF)
-            plan.run(d["src"], d["src_off"], d["tgt"], d["tgt_off"], d["tile_frame"], d["box"], d["box_off"], d["init_T"])
+            if have:
+                plan.run(d["src"], d["src_off"], d["tgt"], d["tgt_off"], d["tile_frame"], d["box"], d["box_off"], d["init_T"])
         torch.cuda.synchronize()
+        del graph                    # before the process group goes away
+        step = step_eager
+        torch.cuda.synchronize()
+        graph_used = True
+    else:
+        graph_used = False
     L.aurdf_icp_profile_enable(0)
-    import ctypes as C
     kms, kn = C.c_double(), C.c_int32()
     L.aurdf_icp_profile_collect(C.byref(kms), C.byref(kn))
     tmax = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
     dev_ms_max = float(tmax.item())
-    frames_per_step = b.n_frames * world
+    frames_per_step = b_all.n_frames if strong else b.n_frames * world
     value = frames_per_step * args.steps / (dev_ms_max * 1e-3)
 
     # ---------------- end to end through the host-buffer C ABI ----------------
@@ -320,25 +398,34 @@ def main():
         keep.append(t)
         return t.numpy()
 
-    hin = [pinned(x) for x in (b.src, b.src_off, b.tgt, b.tgt_off, b.tile_frame, b.box, b.box_off, b.init_T)]
-    B, N = b.n_tiles, b.src.shape[0]
-    out = dict(T=pinned(np.empty((B, 4, 4))), world=pinned(np.empty((N, 3))), corr=pinned(np.empty(N, np.int32)),
-               fitness=pinned(np.empty(B)), rmse=pinned(np.empty(B)), iters=pinned(np.empty(B, np.int32)),
-               ntgt=pinned(np.empty(B, np.int32)))
-    for _ in range(args.warmup):
-        host.run(*hin, out=out)
-    assert np.array_equal(out["iters"], iters.astype(np.int32)), "host path disagrees with the device path"
+    h2d = d2h = 0
+    e2e_s = 0.0
+    if have:
+        hin = [pinned(x) for x in (b.src, b.src_off, b.tgt, b.tgt_off, b.tile_frame, b.box, b.box_off, b.init_T)]
+        B, N = b.n_tiles, b.src.shape[0]
+        out = dict(T=pinned(np.empty((B, 4, 4))), world=pinned(np.empty((N, 3))), corr=pinned(np.empty(N, np.int32)),
+                   fitness=pinned(np.empty(B)), rmse=pinned(np.empty(B)), iters=pinned(np.empty(B, np.int32)),
+                   ntgt=pinned(np.empty(B, np.int32)))
+        for _ in range(args.warmup):
+            host.run(*hin, out=out)
+        assert np.array_equal(out["iters"], iters.astype(np.int32)), "host path disagrees with the device path"
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        host.run(*hin, out=out)
+    if have:
+        for _ in range(args.steps):
+            host.run(*hin, out=out)
     e2e_s = time.perf_counter() - t0
     barrier()
-    h2d, d2h = host.copy_bytes()
-    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if have:
+        h2d, d2h = host.copy_bytes()
+    te = torch.tensor([e2e_s, float(h2d), float(d2h)], dtype=torch.float64, device=dev)
     if world > 1:
+        tsum = te.clone()
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = frames_per_step * args.steps / float(te.item())
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        if strong:                   # strong: bytes of the whole job; weak: per GPU (as the config is)
+            h2d, d2h = int(tsum[1].item()), int(tsum[2].item())
+    e2e_value = frames_per_step * args.steps / float(te[0].item())
     clocks = sampler.stop() if rank == 0 else None
 
     if rank == 0:
@@ -356,10 +443,12 @@ def main():
         instr_per_pair = 8.5
         issue_peak = 148 * 128 * sm_hz
         issue_rate = instr_per_pair * pairs / (k_ms * 1e-3)
-        traffic, traffic_src = load_traffic()
+        small = bool(ns.size and ns.max() <= 320 and ntgt.max() <= 760)
+        kname = "icp_small_kernel" if small else "icp_tiles_kernel"
+        traffic, traffic_src = load_traffic(kname)
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                     "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
-                    "kernel": "icp_small_kernel", "kernel_ms": k_ms,
+                    "kernel": kname, "kernel_ms": k_ms,
                     "kernel_share_of_step": k_ms / (dev_ms / args.steps),
                     "algorithmic_bytes_per_launch": b_alg,
                     "binding_roof": {"bound": "instruction_issue_and_iteration_latency",
@@ -376,25 +465,26 @@ def main():
             modes = cpu_modes(O, b, budget_s=5.0)
             mode = "reference_serial" if modes["reference_serial"]["value"] >= modes["reference_openmp"]["value"] else "reference_openmp"
             cpu = {"value": modes[mode]["value"], "unit": UNIT, "cores": modes[mode]["cores"], "kind": "port",
-                   "sample": REF_SAMPLE.format(w=WORKLOAD, f=b.n_frames, mode=mode) + "; best of repeated runs",
+                   "sample": REF_SAMPLE.format(w=args.workload, f=b.n_frames, mode=mode) + "; best of repeated runs",
                    "modes_frames_per_s": {k: m["value"] for k, m in modes.items()},
+                   "all_core_port_frames_per_s": modes["tile_parallel"]["value"],
                    "host_threads": O.lib().orc_max_threads()}
         print(json.dumps({
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "frames_per_step_per_gpu": b.n_frames,
-                       "points_per_frame": b.meta["n_points"], "clusters": b.n_clusters,
-                       "tiles_per_step_per_gpu": b.n_tiles, "mean_icp_iters": float(iters.mean()),
-                       "l2": "flushed between steps (256 MiB write)",
-                       "parallelism": f"tiles sharded by sequence over {world} GPU(s), all-gather of poses",
-                       "step_launch": "cuda_graph" if graph is not None else "eager"},
+            "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": config_dict(b_all, args.workload, args.scaling, world),
+            "detail": {"mean_icp_iters": float(iters.mean()) if iters.size else 0.0,
+                       "max_icp_iters": int(iters.max()) if iters.size else 0,
+                       "step_launch": "cuda_graph" if graph_used else "eager",
+                       "sharded_equals_single_gpu": check,
+                       "rank0_tiles": int(b.n_tiles)},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": int(L.aurdf_icp_sweep_launches()) * args.steps,
             "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
-        }))
-    if world > 1:
-        dist.destroy_process_group()
+        }), flush=True)
+    host.close()
+    finish(world)
 
 
 if __name__ == "__main__":

@@ -1,0 +1,157 @@
+// Microbenchmark (B200), part 3: the float32 nearest-neighbour scan of icp_small_kernel in isolation,
+// with alternative min-tracking formulations, and the latency of a thread-block-cluster barrier.
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 scan.cu -o scan && ./scan
+// Variants (per PAIR of targets; all share the 2 LDS.128 and the 6 packed f32x2 operations):
+//   V0  keys = (distance bits & ~1023) | index (2 LOP3), best + second best by integer min/max
+//       (4 VIMNMX + 1 VIMNMX3)                                    -- what the kernel does
+//   V1  the same keys, tracked with float min/max (positive floats order like unsigned integers)
+//   V2  keys, best only: one 3-input integer min per pair of targets
+//   V3  no keys (raw distance bits), best + second best           -- cost of tracking without the index
+//   V4  V1 with 3-input float min where it applies
+#include <cstdint>
+#include <cstdio>
+#include <cuda_runtime.h>
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
+
+constexpr int kPairs = 384;
+constexpr uint32_t kIdxMask = 0x3FFu;
+
+template <int V>
+__device__ __forceinline__ void pair_step(const float4 qxy, const float4 qz, const float2 fx2, const float2 fy2,
+                                          const float2 fz2, uint32_t &m1, uint32_t &m2) {
+    const float2 dx = __fadd2_rn(fx2, make_float2(qxy.x, qxy.y));
+    const float2 dy = __fadd2_rn(fy2, make_float2(qxy.z, qxy.w));
+    const float2 dz = __fadd2_rn(fz2, make_float2(qz.x, qz.y));
+    float2 d = __fmul2_rn(dx, dx);
+    d = __ffma2_rn(dy, dy, d);
+    d = __ffma2_rn(dz, dz, d);
+    if (V == 0) {
+        const uint32_t k0 = (__float_as_uint(d.x) & ~kIdxMask) | __float_as_uint(qz.z);
+        const uint32_t k1 = (__float_as_uint(d.y) & ~kIdxMask) | __float_as_uint(qz.w);
+        const uint32_t lo = min(k0, k1), hi = max(k0, k1);
+        m2 = __vimin3_u32(m2, hi, max(m1, lo));
+        m1 = min(m1, lo);
+    } else if (V == 1) {
+        const float k0 = __uint_as_float((__float_as_uint(d.x) & ~kIdxMask) | __float_as_uint(qz.z));
+        const float k1 = __uint_as_float((__float_as_uint(d.y) & ~kIdxMask) | __float_as_uint(qz.w));
+        const float lo = fminf(k0, k1), hi = fmaxf(k0, k1);
+        float f1 = __uint_as_float(m1), f2 = __uint_as_float(m2);
+        f2 = fminf(fminf(f2, hi), fmaxf(f1, lo));
+        f1 = fminf(f1, lo);
+        m1 = __float_as_uint(f1); m2 = __float_as_uint(f2);
+    } else if (V == 2) {
+        const uint32_t k0 = (__float_as_uint(d.x) & ~kIdxMask) | __float_as_uint(qz.z);
+        const uint32_t k1 = (__float_as_uint(d.y) & ~kIdxMask) | __float_as_uint(qz.w);
+        m1 = __vimin3_u32(m1, k0, k1);
+    } else if (V == 3) {
+        const uint32_t k0 = __float_as_uint(d.x), k1 = __float_as_uint(d.y);
+        const uint32_t lo = min(k0, k1), hi = max(k0, k1);
+        m2 = __vimin3_u32(m2, hi, max(m1, lo));
+        m1 = min(m1, lo);
+    } else {
+        const float k0 = __uint_as_float((__float_as_uint(d.x) & ~kIdxMask) | __float_as_uint(qz.z));
+        const float k1 = __uint_as_float((__float_as_uint(d.y) & ~kIdxMask) | __float_as_uint(qz.w));
+        float f1 = __uint_as_float(m1), f2 = __uint_as_float(m2);
+        const float lo = fminf(k0, k1), hi = fmaxf(k0, k1);
+        float t;
+        asm("max.f32 %0, %1, %2;" : "=f"(t) : "f"(f1), "f"(lo));
+        asm("min.f32 %0, %1, %2, %3;" : "=f"(f2) : "f"(f2), "f"(hi), "f"(t));
+        f1 = fminf(f1, lo);
+        m1 = __float_as_uint(f1); m2 = __float_as_uint(f2);
+    }
+}
+
+template <int V>
+__global__ void k_scan(int npairs, int reps, float px, long long *out, uint32_t *sink) {
+    __shared__ float4 sxy[kPairs], sz[kPairs];
+    for (int i = threadIdx.x; i < kPairs; i += blockDim.x) {
+        const float a = 0.001f * i, b = 0.002f * (i ^ 5);
+        sxy[i] = make_float4(-a, -b, -b, -a);
+        sz[i] = make_float4(-a * 0.5f, -b * 0.25f, __uint_as_float(2u * i), __uint_as_float(2u * i + 1));
+    }
+    __syncthreads();
+    const float fx = px + 0.0001f * threadIdx.x, fy = 0.3f * px, fz = 0.7f * px;
+    const float2 fx2 = make_float2(fx, fx), fy2 = make_float2(fy, fy), fz2 = make_float2(fz, fz);
+    uint32_t acc = 0;
+    const int trips2 = (npairs + 1) >> 1;
+    long long t0 = clock64();
+    for (int r = 0; r < reps; ++r) {
+        uint32_t m1 = 0xFFFFFFFFu - r, m2 = 0xFFFFFFFFu;
+        const float4 *pxy = sxy;
+        float4 a0 = pxy[0], a1 = pxy[1];
+        float4 b0 = pxy[kPairs], b1 = pxy[kPairs + 1];
+#pragma unroll 2
+        for (int t = 0; t < trips2; ++t) {
+            pxy += 2;
+            const float4 n0 = pxy[0], n1 = pxy[1];
+            const float4 c0 = pxy[kPairs], c1 = pxy[kPairs + 1];
+            pair_step<V>(a0, b0, fx2, fy2, fz2, m1, m2);
+            pair_step<V>(a1, b1, fx2, fy2, fz2, m1, m2);
+            a0 = n0; a1 = n1; b0 = c0; b1 = c1;
+        }
+        acc += m1 ^ m2;
+    }
+    long long t1 = clock64();
+    if (threadIdx.x == 0) out[blockIdx.x] = t1 - t0;
+    sink[blockIdx.x * blockDim.x + threadIdx.x] = acc;
+}
+
+template <int CS>
+__global__ void k_cluster(int reps, long long *out) {
+    cg::cluster_group cluster = cg::this_cluster();
+    __shared__ double s_x[4];
+    if (threadIdx.x < 4) s_x[threadIdx.x] = threadIdx.x;
+    cluster.sync();
+    long long t0 = clock64();
+    double v = 0;
+    for (int r = 0; r < reps; ++r) {
+        if (threadIdx.x == 0) {   // one DSMEM store to the leader and back, as the cluster ICP variant does
+            double *dst = cluster.map_shared_rank(&s_x[0], 0);
+            dst[(cluster.block_rank() + r) & 3] = v;
+        }
+        cluster.sync();
+        v += cluster.map_shared_rank(&s_x[0], 0)[r & 3];
+        cluster.sync();
+    }
+    long long t1 = clock64();
+    if (threadIdx.x == 0 && blockIdx.x == 0) out[0] = t1 - t0;
+    if (v == 12345.0) out[1] = 1;
+}
+
+template <int CS>
+static void run_cluster(long long *out, int threads) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(CS);
+    cfg.blockDim = dim3(threads);
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    const int reps = 1000;
+    cudaLaunchKernelEx(&cfg, k_cluster<CS>, reps, out);
+    cudaDeviceSynchronize();
+    long long h;
+    cudaMemcpy(&h, out, 8, cudaMemcpyDeviceToHost);
+    printf("cluster of %d CTAs x %d threads: DSMEM store + 2 cluster.sync + DSMEM load : %.1f cycles / round\n", CS, threads,
+           (double)h / reps);
+}
+
+int main() {
+    long long *out; uint32_t *sink;
+    cudaMalloc(&out, 1 << 16); cudaMalloc(&sink, 1 << 24);
+    const int reps = 200;
+    long long h;
+    for (int npairs : {33, 65, 130}) {
+        for (int threads : {32, 128, 256, 768}) {
+#define RUN(V) k_scan<V><<<1, threads>>>(npairs, reps, 0.01f, out, sink); cudaDeviceSynchronize(); \
+    cudaMemcpy(&h, out, 8, cudaMemcpyDeviceToHost); \
+    printf("scan V%d npairs %3d threads %3d: %7.1f cycles / scan, %.2f cycles / pair of targets / warp-per-SMSP\n", V, npairs, \
+           threads, (double)h / reps, (double)h / reps / npairs / ((threads + 127) / 128));
+            RUN(0) RUN(1) RUN(2) RUN(3) RUN(4)
+        }
+    }
+    run_cluster<2>(out, 128); run_cluster<4>(out, 128); run_cluster<8>(out, 128); run_cluster<4>(out, 256);
+    printf("%s\n", cudaGetErrorString(cudaGetLastError()));
+    return 0;
+}

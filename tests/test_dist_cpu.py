@@ -115,3 +115,26 @@ def test_frame_partition_properties():
             assert max(sizes) - min(sizes) <= 2
     sub = b.frame_slice(*frame_partition(b, 2)[1])
     assert sub.tile_frame.min() == 0 and sub.tgt_off[0] == 0 and sub.src_off[0] == 0
+
+
+def test_single_process_share_accepts_tensors_and_rejects_unsorted_frames():
+    """world == 1: the local result may be torch tensors (the CUDA run_local returns device tensors);
+    sharding by frames refuses a batch whose tiles are not frame-major instead of mis-slicing it"""
+    sys.path.insert(0, ROOT)
+    from autourdf_b200 import synth
+    from autourdf_b200.dist import frame_partition, sharded_sweep
+    from oracle import icp_oracle as O
+    O.build()
+    b = synth.make_config("wx200", n_frames=3)
+
+    def run_local(sub):
+        o = O.masked_icp_sweep(sub.src, sub.src_off, sub.tgt, sub.tgt_off, sub.tile_frame, sub.box, sub.box_off,
+                               sub.init_T, nthreads=1)
+        return {k: torch.from_numpy(np.asarray(v)) for k, v in o.items() if k in ("T", "fitness", "rmse", "iters")}
+
+    allr, local, (f0, f1) = sharded_sweep(b, run_local)
+    assert (f0, f1) == (0, b.n_frames) and isinstance(allr["T"], np.ndarray) and allr["T"].shape == (b.n_tiles, 4, 4)
+    assert np.array_equal(allr["T"], local["T"].numpy())
+    b.tile_frame = b.tile_frame[::-1].copy()
+    with pytest.raises(ValueError):
+        frame_partition(b, 2)

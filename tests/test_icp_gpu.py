@@ -201,6 +201,22 @@ def test_sharded_two_ranks_bit_identical_to_single():
     assert all(r[1] for r in res), res
 
 
+def test_single_gpu_sharded_entry_points(synth):
+    """world == 1 through the documented CUDA entry points: sharded_sweep(b, cuda_run_local()) and the
+    device-resident ShardedSweep plan give the plain sweep's poses bit for bit"""
+    import torch
+    from autourdf_b200.dist import ShardedSweep, cuda_run_local, sharded_sweep
+    b = synth.make_config("wx200", n_frames=4)
+    g = cuda_sweep(b)
+    allr, local, span = sharded_sweep(b, cuda_run_local())
+    assert span == (0, b.n_frames) and np.array_equal(allr["T"], g["T"]) and np.array_equal(allr["iters"], g["iters"])
+    for by in ("frames", "tiles"):
+        sh = ShardedSweep(b, torch.device("cuda"), by=by)
+        sh.run()
+        torch.cuda.synchronize()
+        assert np.array_equal(sh.poses(), g["T"])
+
+
 def test_host_path_frame_blocks_match_device_path(synth):
     """aurdf_icp_sweep_host cuts a large batch into frame blocks on separate streams (copies of one
     block overlap the kernels of another); tiles are independent, so every output must be
