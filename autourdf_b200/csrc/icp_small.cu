@@ -460,24 +460,13 @@ icp_small_kernel(const IcpParams p) {
 // host side: launch over all tiles (CTAs of other classes exit at once)
 template <int NT, int MINB, bool DBG>
 static int launch_variant(const IcpParams &P, int n_tiles, cudaStream_t stream) {
-    static bool configured[64] = {};
-    int dev = 0;
-    AURDF_CUDA_CHECK(cudaGetDevice(&dev));
-    if (dev >= 0 && dev < 64 && !configured[dev]) {
-        // MINB x (29.3 KB + static) per SM only fits with the carve-out at its maximum
-        AURDF_CUDA_CHECK(cudaFuncSetAttribute(icp_small_kernel<NT, MINB, DBG>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        configured[dev] = true;
-    }
+    // MINB x (29.3 KB + static) per SM only fits with the carve-out at its maximum (idempotent)
+    AURDF_CUDA_CHECK(cudaFuncSetAttribute(icp_small_kernel<NT, MINB, DBG>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     icp_small_kernel<NT, MINB, DBG><<<n_tiles, NT, kSmallSmemBytes, stream>>>(P);
     return AURDF_OK;
 }
 
-int launch_icp_small(const IcpParams &P, int n_tiles, cudaStream_t stream) {
-    static int minb = -1;   // tuning knob: AURDF_ICP_SMALL_MINB = resident CTAs per SM the kernel is compiled for
-    if (minb < 0) {
-        const char *e = getenv("AURDF_ICP_SMALL_MINB");
-        minb = e ? atoi(e) : 6;
-    }
+int launch_icp_small(const IcpParams &P, int n_tiles, int minb, cudaStream_t stream) {
     if (P.dbg_clock) return launch_variant<128, 5, true>(P, n_tiles, stream);
     if (minb == 7) return launch_variant<128, 7, false>(P, n_tiles, stream);
     if (minb == 5) return launch_variant<128, 5, false>(P, n_tiles, stream);

@@ -16,8 +16,9 @@
 //                         operation order, warp-shuffle reductions, 3x3 Jacobi SVD pose fit,
 //                         SE(3) compose/apply, open3d's convergence rule.
 //
-// Compile with -fmad=false: distances and point transforms must round exactly like the
-// float64 CPU reference (no FMA contraction), otherwise near-tie correspondences flip.
+// Distances and point transforms must round exactly like the float64 CPU reference (no FMA
+// contraction), otherwise near-tie correspondences flip: every such operation is written with the
+// __d*_rn intrinsics, which the compiler never contracts (the file is built with the default -fmad).
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -208,6 +209,7 @@ tile_scan_kernel(const int *__restrict__ cnt, int B, long long capacity, long lo
         status_int[0] = over;
         status_int[1] = (int)(total & 0xffffffffLL);
         status_int[2] = (int)(total >> 32);
+        status_int[3] = 0;   // tile queue of the small-tile kernel
         if (status_user) {
             status_user[0] = over;
             status_user[1] = status_int[1];
@@ -340,7 +342,7 @@ icp_tiles_kernel(const IcpParams p) {
     const int ns = min(ns_tile, lo + per) - lo;
     const int nt = p.cnt[b];
     const long long q0 = p.toff[b];
-    if (p.small_on && tile_is_small(ns_tile, nt)) return;   // icp_small_kernel owns this tile (whole cluster leaves)
+    if (p.small_on && ns_tile <= p.small_ns && nt <= p.small_nt) return;   // the small-tile kernel owns this tile (whole cluster leaves)
     const bool resident = nt <= kQChunk;
     const int nchunks = (nt + kQChunk - 1) / kQChunk;
 
@@ -777,24 +779,42 @@ extern "C" size_t aurdf_icp_workspace_bytes(int32_t n_tiles, int64_t total_src_p
     return make_layout(n_tiles, total_src_points, tgt_capacity).total;
 }
 
-static long long *g_dbg_clock = nullptr;
+// Debug hook of the measurement scripts (scripts/tile_latency.py): per-phase cycle stamps of tile 0.
+// Thread-local, like every other piece of library state: a sweep only sees what its own thread set.
+static thread_local long long *g_dbg_clock = nullptr;
 extern "C" __attribute__((visibility("default"))) void aurdf_debug_set_clock_buffer(void *p) { g_dbg_clock = (long long *)p; }
 
 namespace aurdf {
-int launch_icp_small(const IcpParams &P, int n_tiles, cudaStream_t stream);
+int launch_icp_small(const IcpParams &P, int n_tiles, int minb, cudaStream_t stream);
+int launch_icp_small2(const IcpParams &P, int n_tiles, int minb, cudaStream_t stream);
 }
 
-// AURDF_ICP_SMALL = 0: general kernel only (A/B measurements); anything else: small tiles go to icp_small_kernel
-static int small_variant() {
-    static int v = -1;
-    if (v < 0) {
-        const char *e = getenv("AURDF_ICP_SMALL");
-        v = (e && atoi(e) == 0) ? 0 : 1;
-    }
-    return v;
+// Tuning knobs for A/B measurements, read from the environment once (immutable afterwards; C++11
+// guarantees the initialisation is thread-safe).  Defaults are the measured best.
+//   AURDF_ICP_SMALL        0: general kernel only; 1: icp_small_kernel (round 1); 2: icp_small2_kernel (default)
+//   AURDF_ICP_SMALL_MINB   resident CTAs per SM the small-tile kernel is compiled for
+//   AURDF_ICP_SMALL_SPLIT  0: every round of a tile uses the same lane split (icp_small_kernel only)
+//   AURDF_ICP_STRICT_NT    tiles with at most this many masked targets use the strict pose fit (v2)
+struct Tuning {
+    int small, minb, split, strict_nt;
+};
+static const Tuning &tuning() {
+    static const Tuning t = [] {
+        auto geti = [](const char *name, int dflt) {
+            const char *e = getenv(name);
+            return e ? atoi(e) : dflt;
+        };
+        Tuning v;
+        v.small = geti("AURDF_ICP_SMALL", 2);
+        v.minb = geti("AURDF_ICP_SMALL_MINB", 6);
+        v.split = geti("AURDF_ICP_SMALL_SPLIT", 1);
+        v.strict_nt = geti("AURDF_ICP_STRICT_NT", 32);
+        return v;
+    }();
+    return t;
 }
 
-extern "C" int aurdf_icp_sweep_launches(void) { return small_variant() ? 5 : 4; }
+extern "C" int aurdf_icp_sweep_launches(void) { return tuning().small ? 5 : 4; }
 
 // ---- optional live timing of the dominant kernel (icp_tiles_kernel) --------------------------
 namespace {
@@ -894,15 +914,14 @@ extern "C" int aurdf_icp_sweep(const void *src_xyz, int pts_dtype, const int32_t
     P.out_T = out_T; P.out_world = out_world_xyz; P.out_corr = out_corr; P.out_fit = out_fitness;
     P.out_rmse = out_rmse; P.out_iters = out_iters; P.out_ntgt = out_ntgt;
     P.dbg_clock = g_dbg_clock;
-    P.small_on = small_variant() != 0;
-    {
-        static int split = -1;   // AURDF_ICP_SMALL_SPLIT=0: every round of a tile uses the same lane split (A/B)
-        if (split < 0) {
-            const char *e = getenv("AURDF_ICP_SMALL_SPLIT");
-            split = (e && atoi(e) == 0) ? 0 : 1;
-        }
-        P.split_tail = split;
-    }
+    const Tuning &tn = tuning();
+    P.small_on = tn.small != 0;
+    P.split_tail = tn.split;
+    P.small_ns = tn.small == 2 ? kS2Ns : kSmNs;
+    P.small_nt = kSmNt32;
+    P.n_tiles = n_tiles;
+    P.queue = status_int + 3;
+    P.strict_nt = tn.strict_nt;
     EvPair ev{nullptr, nullptr};
     if (g_prof_on) {
         AURDF_CUDA_CHECK(cudaEventCreate(&ev.a));
@@ -912,7 +931,7 @@ extern "C" int aurdf_icp_sweep(const void *src_xyz, int pts_dtype, const int32_t
     // small tiles first (one CTA each, all resident at once); the general kernel's CTAs for those
     // tiles exit immediately, and vice versa
     if (P.small_on) {
-        const int rc = launch_icp_small(P, n_tiles, stream);
+        const int rc = tn.small == 2 ? launch_icp_small2(P, n_tiles, tn.minb, stream) : launch_icp_small(P, n_tiles, tn.minb, stream);
         if (rc != AURDF_OK) return rc;
     }
     if (use_cluster) {

@@ -64,7 +64,8 @@ __device__ __forceinline__ void pair_step(const float4 qxy, const float4 qz, con
 
 template <int V>
 __global__ void k_scan(int npairs, int reps, float px, long long *out, uint32_t *sink) {
-    __shared__ float4 sxy[kPairs], sz[kPairs];
+    __shared__ float4 sall[2 * kPairs];
+    float4 *sxy = sall, *sz = sall + kPairs;
     for (int i = threadIdx.x; i < kPairs; i += blockDim.x) {
         const float a = 0.001f * i, b = 0.002f * (i ^ 5);
         sxy[i] = make_float4(-a, -b, -b, -a);
@@ -102,6 +103,7 @@ __global__ void k_cluster(int reps, long long *out) {
     cg::cluster_group cluster = cg::this_cluster();
     __shared__ double s_x[4];
     if (threadIdx.x < 4) s_x[threadIdx.x] = threadIdx.x;
+    __syncthreads();
     cluster.sync();
     long long t0 = clock64();
     double v = 0;

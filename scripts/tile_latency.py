@@ -60,6 +60,10 @@ if os.environ.get("AURDF_ICP_SMALL", "128") != "0":
     ids = {0: "iteration start", 1: "P update", 2: "float32 scan", 3: "merge+certificate+exact distance", 4: "exact rescan branch",
            5: "pass end", 6: "barrier 1", 7: "moment reduction", 8: "barrier 2", 20: "totals+covariance", 21: "rotation fit",
            9: "translation+store U (fit done)"}
+    if os.environ.get("AURDF_ICP_SMALL", "2") == "2":   # icp_small2_kernel
+        ids = {0: "iteration start", 1: "P update", 2: "cache test", 3: "float32 scan (misses)", 4: "merge+certificate+exact distance",
+               5: "pass end", 7: "moment reduction", 8: "barrier A", 20: "totals+covariance", 21: "rotation fit",
+               9: "translation+store U (fit done)"}
     c = c.reshape(-1, 2)
     c = c[c[:, 0] > 0]
     from collections import OrderedDict
