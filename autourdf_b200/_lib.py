@@ -42,6 +42,7 @@ SIGNATURES = {
     "aurdf_se3_to_local": (C.c_int, [_vp, _vp, _vp, _i32, _i64, _vp, _vp]),
     "aurdf_resample_clusters": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _f64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "aurdf_dq_op": (C.c_int, [C.c_int, _vp, _vp, _vp, _vp, _i64, C.c_int, _vp]),
+    "aurdf_dq_op_bwd": (C.c_int, [C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _i64, C.c_int, _vp]),
     "aurdf_coord_dist_map_workspace_bytes": (_sz, [_i32, _i32, _i32]),
     "aurdf_coord_dist_map": (C.c_int, [_vp, _i32, _i32, _f64, _i32, _vp, _vp, _vp, _sz, _vp]),
 }

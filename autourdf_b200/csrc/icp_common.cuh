@@ -387,26 +387,74 @@ __device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, 
 __device__ __forceinline__ double dvd(double a, double b) { return __ddiv_rn(a, b); }
 __device__ __forceinline__ double sqr(double a) { return __dsqrt_rn(a); }
 
-// rows p,q of M <- [c s; -s c] from the left;  cols p,q of M <- M [c s; -s c]
-__device__ __forceinline__ void rot_rows(double (&M)[3][3], int p, int q, double c, double s) {
+// rows P,Q of M <- [c s; -s c] from the left;  cols P,Q of M <- M [c s; -s c]  (static indices: registers)
+template <int P, int Q>
+__device__ __forceinline__ void rot_rows(double (&M)[3][3], double c, double s) {
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
-        const double x = M[p][j], y = M[q][j];
-        M[p][j] = add(mul(c, x), mul(s, y));
-        M[q][j] = add(mul(-s, x), mul(c, y));
+        const double x = M[P][j], y = M[Q][j];
+        M[P][j] = add(mul(c, x), mul(s, y));
+        M[Q][j] = add(mul(-s, x), mul(c, y));
     }
 }
-__device__ __forceinline__ void rot_cols(double (&M)[3][3], int p, int q, double c, double s) {
+template <int P, int Q>
+__device__ __forceinline__ void rot_cols(double (&M)[3][3], double c, double s) {
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
-        const double x = M[i][p], y = M[i][q];
-        M[i][p] = sub(mul(c, x), mul(s, y));
-        M[i][q] = add(mul(s, x), mul(c, y));
+        const double x = M[i][P], y = M[i][Q];
+        M[i][P] = sub(mul(c, x), mul(s, y));
+        M[i][Q] = add(mul(s, x), mul(c, y));
+    }
+}
+
+// one two-sided Jacobi step on the index pair (Q, P), Q < P, exactly as in orc_svd3
+template <int P, int Q>
+__device__ __forceinline__ void jacobi_step(double (&W)[3][3], double (&U)[3][3], double (&V)[3][3], double &maxdiag,
+                                            bool &finished) {
+    const double precision = 2.0 * 2.220446049250313e-16;
+    const double tiny = 2.2250738585072014e-308;
+    const double thr = fmax(tiny, mul(precision, maxdiag));
+    if (!(fabs(W[P][Q]) > thr || fabs(W[Q][P]) > thr)) return;
+    finished = false;
+    const double m00 = W[Q][Q], m01 = W[Q][P], m10 = W[P][Q], m11 = W[P][P];
+    const double t = add(m00, m11), d = sub(m10, m01);
+    double c1, s1;
+    if (fabs(d) < tiny) { c1 = 1.0; s1 = 0.0; }
+    else {
+        const double u = dvd(t, d), tmp = sqr(add(1.0, mul(u, u)));
+        s1 = dvd(1.0, tmp); c1 = dvd(u, tmp);
+    }
+    const double a00 = add(mul(c1, m00), mul(s1, m10)), a01 = add(mul(c1, m01), mul(s1, m11));
+    const double a11 = add(mul(-s1, m01), mul(c1, m11));
+    double c2, s2;
+    if (fabs(a01) < tiny) { c2 = 1.0; s2 = 0.0; }
+    else {
+        const double tau = dvd(sub(a00, a11), mul(2.0, a01)), w = sqr(add(mul(tau, tau), 1.0));
+        const double tn = (tau >= 0) ? dvd(-1.0, add(tau, w)) : dvd(-1.0, sub(tau, w));
+        c2 = dvd(1.0, sqr(add(mul(tn, tn), 1.0)));
+        s2 = mul(tn, c2);
+    }
+    const double cl = add(mul(c2, c1), mul(s2, s1));
+    const double sl = sub(mul(c2, s1), mul(s2, c1));
+    rot_rows<Q, P>(W, cl, sl);
+    rot_cols<Q, P>(W, c2, s2);
+    rot_cols<Q, P>(U, cl, -sl);
+    rot_cols<Q, P>(V, c2, s2);
+    maxdiag = fmax(maxdiag, fmax(fabs(W[P][P]), fabs(W[Q][Q])));
+}
+
+template <int I, int K>
+__device__ __forceinline__ void swap_sv(double (&S)[3], double (&U)[3][3], double (&V)[3][3]) {
+    double t = S[I]; S[I] = S[K]; S[K] = t;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        t = U[r][I]; U[r][I] = U[r][K]; U[r][K] = t;
+        t = V[r][I]; V[r][I] = V[r][K]; V[r][K] = t;
     }
 }
 
 // A = U diag(S) V^T exactly as orc_svd3 computes it
-static __device__ __noinline__ void svd3(const double (&A)[3][3], double (&U)[3][3], double (&S)[3], double (&V)[3][3]) {
+__device__ __forceinline__ void svd3(const double (&A)[3][3], double (&U)[3][3], double (&S)[3], double (&V)[3][3]) {
     double W[3][3];
     double scale = 0.0;
 #pragma unroll
@@ -422,63 +470,35 @@ static __device__ __noinline__ void svd3(const double (&A)[3][3], double (&U)[3]
     for (int i = 0; i < 3; ++i)
 #pragma unroll
         for (int j = 0; j < 3; ++j) W[i][j] = dvd(A[i][j], scale);
-    const double precision = 2.0 * 2.220446049250313e-16;
-    const double tiny = 2.2250738585072014e-308;
     double maxdiag = fmax(fabs(W[0][0]), fmax(fabs(W[1][1]), fabs(W[2][2])));
     bool finished = false;
+#pragma unroll 1
     for (int sweeps = 0; !finished && sweeps < 64; ++sweeps) {
         finished = true;
-#pragma unroll 1
-        for (int pq = 0; pq < 3; ++pq) {
-            const int p = pq == 0 ? 1 : 2, q = pq == 2 ? 1 : 0;   // (1,0), (2,0), (2,1)
-            const double thr = fmax(tiny, mul(precision, maxdiag));
-            if (fabs(W[p][q]) > thr || fabs(W[q][p]) > thr) {
-                finished = false;
-                const double m00 = W[q][q], m01 = W[q][p], m10 = W[p][q], m11 = W[p][p];
-                const double t = add(m00, m11), d = sub(m10, m01);
-                double c1, s1;
-                if (fabs(d) < tiny) { c1 = 1.0; s1 = 0.0; }
-                else {
-                    const double u = dvd(t, d), tmp = sqr(add(1.0, mul(u, u)));
-                    s1 = dvd(1.0, tmp); c1 = dvd(u, tmp);
-                }
-                const double a00 = add(mul(c1, m00), mul(s1, m10)), a01 = add(mul(c1, m01), mul(s1, m11));
-                const double a11 = add(mul(-s1, m01), mul(c1, m11));
-                double c2, s2;
-                if (fabs(a01) < tiny) { c2 = 1.0; s2 = 0.0; }
-                else {
-                    const double tau = dvd(sub(a00, a11), mul(2.0, a01)), w = sqr(add(mul(tau, tau), 1.0));
-                    const double tn = (tau >= 0) ? dvd(-1.0, add(tau, w)) : dvd(-1.0, sub(tau, w));
-                    c2 = dvd(1.0, sqr(add(mul(tn, tn), 1.0)));
-                    s2 = mul(tn, c2);
-                }
-                const double cl = add(mul(c2, c1), mul(s2, s1));
-                const double sl = sub(mul(c2, s1), mul(s2, c1));
-                rot_rows(W, q, p, cl, sl);
-                rot_cols(W, q, p, c2, s2);
-                rot_cols(U, q, p, cl, -sl);
-                rot_cols(V, q, p, c2, s2);
-                maxdiag = fmax(maxdiag, fmax(fabs(W[p][p]), fabs(W[q][q])));
-            }
-        }
+        jacobi_step<1, 0>(W, U, V, maxdiag, finished);
+        jacobi_step<2, 0>(W, U, V, maxdiag, finished);
+        jacobi_step<2, 1>(W, U, V, maxdiag, finished);
     }
+#pragma unroll
     for (int i = 0; i < 3; ++i) {
         const double a = fabs(W[i][i]);
         S[i] = a;
-        if (a != 0.0 && W[i][i] < 0.0)
+        if (a != 0.0 && W[i][i] < 0.0) {
+#pragma unroll
             for (int r = 0; r < 3; ++r) U[r][i] = -U[r][i];
+        }
     }
+#pragma unroll
     for (int i = 0; i < 3; ++i) S[i] = mul(S[i], scale);
-    for (int i = 0; i < 3; ++i) {   // selection sort, descending
-        int k = i;
-        for (int j = i + 1; j < 3; ++j)
-            if (S[j] > S[k]) k = j;
-        if (S[k] == 0.0) break;
-        if (k != i) {
-            double t = S[i]; S[i] = S[k]; S[k] = t;
-            for (int r = 0; r < 3; ++r) {
-                t = U[r][i]; U[r][i] = U[r][k]; U[r][k] = t;
-                t = V[r][i]; V[r][i] = V[r][k]; V[r][k] = t;
+    // selection sort, descending, stopping at the first zero maximum (orc_svd3), with static indices
+    {
+        const int k = (S[1] > S[0]) ? ((S[2] > S[1]) ? 2 : 1) : ((S[2] > S[0]) ? 2 : 0);
+        const double sk = k == 0 ? S[0] : (k == 1 ? S[1] : S[2]);
+        if (sk != 0.0) {
+            if (k == 1) swap_sv<0, 1>(S, U, V);
+            else if (k == 2) swap_sv<0, 2>(S, U, V);
+            if (S[2] > S[1]) {
+                if (S[2] != 0.0) swap_sv<1, 2>(S, U, V);
             }
         }
     }
@@ -492,19 +512,28 @@ __device__ __forceinline__ double det3s(const double (&M)[3][3]) {   // the orac
 }
 
 // update U (row-major 3x4 into Um[12]) from the two-pass covariance sigma and the means; kabsch_sv of the oracle
-static __device__ __noinline__ void pose_from_sigma(const double (&sigma)[3][3], const double (&ms)[3], const double (&md)[3],
+static __device__ __noinline__ void pose_from_sigma(const double (&sigma_in)[3][3], const double (&ms)[3], const double (&md)[3],
                                                     double *Um) {
-    double U[3][3], S[3], V[3][3], R[3][3];
+    double sigma[3][3], U[3][3], S[3], V[3][3], R[3][3];   // local copies: everything below stays in registers
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) sigma[i][j] = sigma_in[i][j];
     svd3(sigma, U, S, V);
     const double D[3] = {1.0, 1.0, (mul(det3s(U), det3s(V)) < 0) ? -1.0 : 1.0};
+#pragma unroll
     for (int r = 0; r < 3; ++r)
+#pragma unroll
         for (int c = 0; c < 3; ++c) {
             double s = 0.0;
+#pragma unroll
             for (int k = 0; k < 3; ++k) s = add(s, mul(mul(U[r][k], D[k]), V[c][k]));
             R[r][c] = s;
         }
+#pragma unroll
     for (int r = 0; r < 3; ++r) {
         double rm = 0.0;
+#pragma unroll
         for (int k = 0; k < 3; ++k) rm = add(rm, mul(R[r][k], ms[k]));
         Um[4 * r + 0] = R[r][0];
         Um[4 * r + 1] = R[r][1];
@@ -551,8 +580,7 @@ constexpr int kSmPairs = 384;  // float32 target pairs in shared memory, incl. t
 constexpr int kSmNt32 = 2 * kSmPairs - 8;   // most masked targets of a small tile (760)
 constexpr int kSmNt64 = 384;   // most targets whose float64 copy also lives in shared memory
 __device__ __forceinline__ bool tile_is_small(int ns, int nt) { return ns <= kSmNs && nt <= kSmNt32; }
-constexpr int kS2Ns = 256;     // small-tile kernel v2: most source points (two rounds of 128 home slots)
-constexpr int kS2Nt64 = 352;   // v2: most targets whose float64 copy lives in shared memory
+constexpr int kS2Ns = 384;     // small-tile kernel v2: most source points (three rounds of 128 home slots)
 
 // x' = ((m0 x + m1 y) + m2 z) + m3, each operation rounded (open3d PointCloud::Transform)
 __device__ __forceinline__ double affine_row(const double *m, double x, double y, double z) {

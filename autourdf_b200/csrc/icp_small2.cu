@@ -16,7 +16,7 @@
 //     (S lanes per point), so a warp with 8 misses scans a quarter as long;
 //   * the pose fit works on the unnormalised covariance n*S_ba - S_b S_a^T (no division before the
 //     Newton iteration; 1/n is only needed for the translation and is computed beside it);
-//   * rank-deficient tiles (a box that holds a handful of targets) fit their poses in "strict" mode:
+//   * tiles whose box holds a handful of targets (rank-deficient fits) fit their poses in "strict" mode:
 //     the CPU reference's arithmetic operation for operation (icp_common.cuh, namespace strict), so
 //     they too are bit-comparable instead of being a different member of a one-parameter family.
 // The float32 scan itself (packed f32x2 arithmetic, keyed min tracking, certified against float64) is
@@ -36,9 +36,14 @@ constexpr int kWarps = kNT / 32;
 constexpr uint32_t kIdxMask2 = 0x3FFu;   // low mantissa bits of a key hold the target index (< 1024)
 static_assert(2 * kSmPairs <= 1024, "index field");
 
-constexpr size_t kSmall2SmemBytes = (size_t)kSmPairs * 2 * sizeof(float4) + (size_t)3 * kS2Nt64 * sizeof(double) +
-                                    (size_t)4 * kS2Ns * sizeof(double) + (size_t)kS2Ns * sizeof(float4) +
-                                    (size_t)kS2Ns * sizeof(int) + (size_t)kWarps * 32 * sizeof(float4);
+// Shared memory of a CTA: the float32 target pairs, the per-warp scan lists, and a pool that every tile
+// lays out for itself -- 52 bytes of state per home slot (128 slots per round of source points), then the
+// float64 targets if they still fit (otherwise they are read from the compacted arrays in L2).
+// 6 CTAs per SM: 6 x (36096 + 1360 static + 1024 reserved) <= 233472.
+constexpr size_t kSlotBytes = sizeof(float4) + 4 * sizeof(double) + sizeof(int);
+constexpr size_t kPoolBytes = 21760;
+constexpr size_t kSmall2SmemBytes = (size_t)kSmPairs * 2 * sizeof(float4) + (size_t)kWarps * 32 * sizeof(float4) + kPoolBytes;
+static_assert((size_t)kS2Ns * kSlotBytes <= kPoolBytes, "the per-slot state of the largest small tile must fit");
 
 // home slot t = 128 r + 32 w + l  <->  source point 128 r + 4 l + w (round r, warp w, lane l)
 __device__ __forceinline__ int slot_to_point(int t) { return (t & ~127) + 4 * (t & 31) + ((t >> 5) & 3); }
@@ -51,16 +56,10 @@ icp_small2_kernel(const IcpParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float4 *sxy = reinterpret_cast<float4 *>(smem_raw);             // (-x0, -x1, -y0, -y1) of a target pair
     float4 *sz = sxy + kSmPairs;                                    // (-z0, -z1, bits: index of target 0, of target 1)
-    double *sqx = reinterpret_cast<double *>(sz + kSmPairs);        // float64 targets (n_t <= kS2Nt64)
-    double *sqy = sqx + kS2Nt64;
-    double *sqz = sqy + kS2Nt64;
-    double *spx = sqz + kS2Nt64;                                    // current source points, by home slot
-    double *spy = spx + kS2Ns;
-    double *spz = spy + kS2Ns;
-    double *sbd = spz + kS2Ns;                                      // exact squared distance to the nearest target
-    float4 *sanc = reinterpret_cast<float4 *>(sbd + kS2Ns);         // cache: anchor (float32, about the origin), rho
-    int *scj = reinterpret_cast<int *>(sanc + kS2Ns);               // nearest target (compacted index) or -1
-    float4 *slist = reinterpret_cast<float4 *>(scj + kS2Ns);        // per warp: points to scan (x, y, z, slot bits)
+    float4 *slist = sz + kSmPairs;                                  // per warp: points to scan (x, y, z, slot bits)
+    // the rest of the pool is laid out per tile: per-slot state (128 slots per round), then -- if they
+    // still fit -- the float64 targets
+    unsigned char *pool = reinterpret_cast<unsigned char *>(slist + kWarps * 32);
 
     __shared__ double s_part[kWarps][4][6];   // per-warp moment products M[0..3][0..5] of the current pass
     __shared__ double s_tot[16];              // their totals, M[r][c] at 4 r + c (fit warp only)
@@ -107,9 +106,19 @@ icp_small2_kernel(const IcpParams p) {
         if constexpr (DBG) dbg_on = b == 0;
         const long long q0 = p.toff[b];
         const double *gqx = p.qx + q0, *gqy = p.qy + q0, *gqz = p.qz + q0;
-        const bool q64s = nt <= kS2Nt64;      // float64 targets fit in shared memory
+        const int rounds_ = (ns + kNT - 1) / kNT, nslot = rounds_ * kNT, nte = (nt + 1) & ~1;
+        float4 *sanc = reinterpret_cast<float4 *>(pool);            // cache: anchor (float32, about the origin), rho
+        double *spx = reinterpret_cast<double *>(sanc + nslot);     // current source points, by home slot
+        double *spy = spx + nslot;
+        double *spz = spy + nslot;
+        double *sbd = spz + nslot;                                  // exact squared distance to the nearest target
+        int *scj = reinterpret_cast<int *>(sbd + nslot);            // nearest target (compacted index) or -1
+        double *sqx = reinterpret_cast<double *>(scj + nslot);      // float64 targets, if the pool has room for them
+        double *sqy = sqx + nte;
+        double *sqz = sqy + nte;
+        const bool q64s = (size_t)nslot * kSlotBytes + (size_t)nte * 24 <= kPoolBytes;
         const double *qxp = q64s ? sqx : gqx, *qyp = q64s ? sqy : gqy, *qzp = q64s ? sqz : gqz;
-        const int rounds = (ns + kNT - 1) / kNT;
+        const int rounds = rounds_;
 
         if (tid < 16) {
             s_T[tid] = p.init_T[16 * (size_t)b + tid];
@@ -205,6 +214,12 @@ icp_small2_kernel(const IcpParams p) {
             for (int r = 0; r < rounds; ++r) {
                 const int t = r * kNT + tid;
                 const bool active = r * kNT + 4 * lane + warp < ns;
+                // everything the cache test needs is loaded before the move (independent of it): the anchor,
+                // the previous winner and its coordinates
+                const float4 an = sanc[t];
+                const int j1c = max(scj[t], 0);
+                double qx1 = 0.0, qy1 = 0.0, qz1 = 0.0;
+                if (nt > 0) { qx1 = qxp[j1c]; qy1 = qyp[j1c]; qz1 = qzp[j1c]; }   // tile-uniform branch
                 double x = 0.0, y = 0.0, z = 0.0;
                 if (active) {
                     x = spx[t]; y = spy[t]; z = spz[t];
@@ -216,22 +231,19 @@ icp_small2_kernel(const IcpParams p) {
                 if (r == 0) stamp(1);   // P update done
                 const float fx = (float)(x - ox), fy = (float)(y - oy), fz = (float)(z - oz);
                 bool miss = active && nt > 0;
-                if (miss) {
+                {
                     // cache test: the winner of the last scan is still the float64 argmin if
                     // d(p, winner) + |p - anchor| < rho (rho: lower bound on the distance from the anchor
                     // to every other target).  float32 arithmetic, every rounding over-covered 100-fold.
-                    const float4 an = sanc[t];
-                    if (an.w > 0.f) {
-                        const int j1 = scj[t];
-                        const double D1 = exact_d2(x, y, z, j1);
-                        const float ex = fx - an.x, ey = fy - an.y, ez = fz - an.z;
-                        const float del = sqrtf(fmaf(ez, ez, fmaf(ey, ey, ex * ex)));
-                        const float amag = fmaxf(aq, fmaxf(fabsf(fx), fmaxf(fabsf(fy), fabsf(fz))));
-                        const float lhs = (sqrtf((float)D1) + del) * 1.0001f + 1e-6f * (amag + del);
-                        if (lhs < an.w) {
-                            miss = false;
-                            sbd[t] = D1;
-                        }
+                    const double dx = __dsub_rn(x, qx1), dy = __dsub_rn(y, qy1), dz = __dsub_rn(z, qz1);
+                    const double D1 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+                    const float ex = fx - an.x, ey = fy - an.y, ez = fz - an.z;
+                    const float del = sqrtf(fmaf(ez, ez, fmaf(ey, ey, ex * ex)));
+                    const float amag = fmaxf(aq, fmaxf(fabsf(fx), fmaxf(fabsf(fy), fabsf(fz))));
+                    const float lhs = (sqrtf((float)D1) + del) * 1.0001f + 1e-6f * (amag + del);
+                    if (miss && an.w > 0.f && lhs < an.w) {
+                        miss = false;
+                        sbd[t] = D1;
                     }
                 }
                 if (r == 0) stamp(2);   // cache test done
@@ -241,7 +253,7 @@ icp_small2_kernel(const IcpParams p) {
                 if (miss) slist[warp * 32 + __popc(mb & lt_mask)] = make_float4(fx, fy, fz, __int_as_float(t));
                 __syncwarp();
                 int ls = 0;
-                while ((1 << ls) < S_cap && n * (2 << ls) <= 32) ++ls;
+                while ((2 << ls) <= S_cap && n * (2 << ls) <= 32) ++ls;
                 const int S = 1 << ls;                 // lanes per point: the warp's misses share its 32 lanes
                 const int sub = lane & (S - 1);
                 const int e = lane >> ls;
@@ -366,31 +378,40 @@ icp_small2_kernel(const IcpParams p) {
             const double *pu = gid == 1 ? qxp : (gid == 2 ? qyp : qzp);
             const double *pw = gid == 1 ? spx : (gid == 2 ? spy : (gid == 3 ? spz : sbd));
             const double oc = gid == 1 ? ox : (gid == 2 ? oy : (gid == 3 ? oz : 0.0));
-            // operand = (value - oc) * mul + add: row/column 0 is the constant 1, rows >= 4 and columns >= 5 are 0
+            // operand = ((value - oc) * mul + add1) * matched: row / column 0 is the constant 1, rows >= 4 and
+            // columns >= 5 are 0, an unmatched point contributes nothing.  Pure arithmetic: lanes of one warp
+            // must not take different branches around the mma.
             const double mul_u = (gid >= 1 && gid < 4) ? 1.0 : 0.0, mul_w = (gid >= 1 && gid < 5) ? 1.0 : 0.0;
             const double add1 = gid == 0 ? 1.0 : 0.0;
             double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
             for (int r = 0; r < rounds; ++r) {
                 const int base = r * kNT + 32 * warp + tig;
-                const int left = ns - r * kNT - warp;         // home points of this warp in this round: ceil(left / 4), at most 32
-                const int ngrp = left <= 0 ? 0 : min(8, (left + 15) >> 4);
+                // all loads of the round first (the slots past the warp's last home point hold j = -1), then
+                // the eight products back to back: the load latencies are paid once, not once per group
+                int jj[8];
+                double okf[8], u[8], w[8];
 #pragma unroll
                 for (int g = 0; g < 8; ++g) {
-                    if (g < ngrp) {   // warp-uniform
-                        const int t = base + 4 * g;
-                        const int j = scj[t];
-                        const double d2 = sbd[t];
-                        const bool ok = j >= 0 && d2 < p.r2;
-                        const int jc = ok ? j : 0;
-                        double u = (pu[jc] - oc) * mul_u + add1;
-                        double w = (pw[t] - oc) * mul_w + add1;                 // column 4 = d^2 (oc = 0)
-                        u = ok ? u : 0.0;                                        // unmatched point: zero row and column entry
-                        w = ok ? w : 0.0;
-                        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
-                                     : "+d"(acc[g & 1][0]), "+d"(acc[g & 1][1]) : "d"(u), "d"(w));
-                    }
+                    jj[g] = scj[base + 4 * g];
+                    okf[g] = sbd[base + 4 * g];
+                    w[g] = pw[base + 4 * g];
+                }
+                stamp(30);   // reduce: first loads issued
+#pragma unroll
+                for (int g = 0; g < 8; ++g) {
+                    const bool ok = jj[g] >= 0 && okf[g] < p.r2;
+                    u[g] = pu[max(jj[g], 0)];
+                    okf[g] = ok ? 1.0 : 0.0;
+                }
+#pragma unroll
+                for (int g = 0; g < 8; ++g) {
+                    const double uu = fma(u[g] - oc, mul_u, add1) * okf[g];
+                    const double ww = fma(w[g] - oc, mul_w, add1) * okf[g];   // column 4 = d^2 (oc = 0)
+                    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                                 : "+d"(acc[g & 1][0]), "+d"(acc[g & 1][1]) : "d"(uu), "d"(ww));
                 }
             }
+            stamp(31);   // reduce: products done
             const double d0 = acc[0][0] + acc[1][0], d1 = acc[0][1] + acc[1][1];
             // this lane holds M[gid][2 tig] and M[gid][2 tig + 1]
             if (gid < 4 && tig < 3) {
@@ -402,10 +423,9 @@ icp_small2_kernel(const IcpParams p) {
         // ---- pose fit (warp 0) ----
         bool have_warm = false;
         // fast path, lane 0: Newton on SO(3) from the unnormalised covariance; false = not certifiable
-        auto fit_fast = [&](bool first) -> bool {
+        auto fit_fast = [&]() {
             const double *t = s_tot;   // t[4 r + c] = sum u_r w_c
             double Um[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
-            bool ok = true;
             if (t[0] > 0.0) {
                 const double n = t[0];
                 double sigma[3][3], R[3][3];
@@ -414,12 +434,10 @@ icp_small2_kernel(const IcpParams p) {
 #pragma unroll
                     for (int cc = 0; cc < 3; ++cc) sigma[r][cc] = n * t[4 * (r + 1) + cc + 1] - t[4 * (r + 1)] * t[cc + 1];
                 stamp(20);   // totals loaded, covariance formed
-                ok = kabsch_rotation_newton4(sigma, R);
-                if (ok || !first) {
-                    if (!ok) {   // reflection / rank-deficient / large step later in the run: Jacobi SVD, warm-started
+                {
+                    if (!kabsch_rotation_newton4(sigma, R)) {   // reflection / rank-deficient / large step: Jacobi SVD, warm-started
                         kabsch_rotation(sigma, R, s_warm, have_warm);
                         have_warm = true;
-                        ok = true;
                     }
                     stamp(21);   // rotation fitted
                     const double inv = rcp_raw2(n);
@@ -434,54 +452,73 @@ icp_small2_kernel(const IcpParams p) {
                     }
                 }
             }
-            if (ok) {
 #pragma unroll
-                for (int k = 0; k < 12; ++k) s_U[k] = Um[k];
-            }
-            return ok;
+            for (int k = 0; k < 12; ++k) s_U[k] = Um[k];
         };
         // strict path, whole warp 0: the CPU reference's two-pass sums in ascending source index, one
         // accumulator per lane, then its Jacobi SVD on lane 0 (icp_common.cuh, namespace strict)
         auto fit_strict = [&]() {
-            double acc = 0.0;
-            int c = 0;
-            const double *src1 = lane == 0 ? spx : (lane == 1 ? spy : (lane == 2 ? spz : (lane == 3 ? qxp : (lane == 4 ? qyp : qzp))));
-            for (int i = 0; i < ns; ++i) {
-                const int t = point_to_slot(i);
-                const int j = scj[t];
-                if (j >= 0 && sbd[t] < p.r2) {
-                    ++c;
-                    if (lane < 6) acc = strict::add(acc, src1[lane < 3 ? t : j]);
+            // Sums over the matched points in ascending source index.  Sixteen points at a time: lane l stages
+            // the addends of point c0 + l in shared memory (one padded row per accumulator), then accumulator
+            // lane k adds row k in order -- its loads are independent, only the adds form a chain.
+            double *stage = reinterpret_cast<double *>(slist);   // [9][17]; the other warps wait at barrier B
+            auto ordered_sum = [&](int nacc, auto addends, int &count) {
+                double acc = 0.0;
+                count = 0;
+                for (int c0 = 0; c0 < ns; c0 += 16) {
+                    const int i = c0 + (lane & 15);
+                    int t = 0, j = 0;
+                    bool ok = false;
+                    if (lane < 16 && i < ns) {
+                        t = point_to_slot(i);
+                        j = scj[t];
+                        ok = j >= 0 && sbd[t] < p.r2;
+                    }
+                    const unsigned m = __ballot_sync(0xffffffffu, ok);
+                    count += __popc(m);
+                    if (ok) addends(t, j, stage + lane);
+                    __syncwarp();
+                    if (lane < nacc) {
+                        double v[16];
+#pragma unroll
+                        for (int q = 0; q < 16; ++q) v[q] = stage[lane * 17 + q];
+#pragma unroll
+                        for (int q = 0; q < 16; ++q)
+                            if ((m >> q) & 1u) acc = strict::add(acc, v[q]);
+                    }
+                    __syncwarp();
                 }
-            }
+                return acc;
+            };
+            int c = 0;
+            const double sum1 = ordered_sum(6, [&](int t, int j, double *row) {
+                row[0] = spx[t]; row[17] = spy[t]; row[34] = spz[t];
+                row[51] = qxp[j]; row[68] = qyp[j]; row[85] = qzp[j]; }, c);
             double Um[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
             if (c > 0) {   // warp-uniform
                 const double one_over_n = strict::dvd(1.0, (double)c);
-                const double mean = strict::mul(acc, one_over_n);   // lanes 0-2: source mean, 3-5: target mean
-                const int rr = lane / 3, cc = lane - 3 * rr;         // lanes 0-8: covariance entry (rr, cc)
-                const double ms_c = __shfl_sync(0xffffffffu, mean, cc < 3 ? cc : 0);
-                const double md_r = __shfl_sync(0xffffffffu, mean, rr < 3 ? 3 + rr : 3);
-                const double *pa = cc == 0 ? spx : (cc == 1 ? spy : spz);
-                const double *pb = rr == 0 ? qxp : (rr == 1 ? qyp : qzp);
-                double sg = 0.0;
-                if (lane < 9) {
-                    for (int i = 0; i < ns; ++i) {
-                        const int t = point_to_slot(i);
-                        const int j = scj[t];
-                        if (j >= 0 && sbd[t] < p.r2)
-                            sg = strict::add(sg, strict::mul(strict::sub(pb[j], md_r), strict::sub(pa[t], ms_c)));
-                    }
-                    sg = strict::mul(sg, one_over_n);
-                }
-                double sigma[3][3], ms[3], md[3];
-#pragma unroll
-                for (int k = 0; k < 9; ++k) sigma[k / 3][k % 3] = __shfl_sync(0xffffffffu, sg, k);
+                const double mean = strict::mul(sum1, one_over_n);   // lanes 0-2: source mean, 3-5: target mean
+                double ms[3], md[3];
 #pragma unroll
                 for (int k = 0; k < 3; ++k) {
                     ms[k] = __shfl_sync(0xffffffffu, mean, k);
                     md[k] = __shfl_sync(0xffffffffu, mean, 3 + k);
                 }
+                int c2 = 0;
+                double sg = ordered_sum(9, [&](int t, int j, double *row) {
+                    const double a[3] = {strict::sub(spx[t], ms[0]), strict::sub(spy[t], ms[1]), strict::sub(spz[t], ms[2])};
+                    const double bb[3] = {strict::sub(qxp[j], md[0]), strict::sub(qyp[j], md[1]), strict::sub(qzp[j], md[2])};
+#pragma unroll
+                    for (int r = 0; r < 3; ++r)
+#pragma unroll
+                        for (int cc = 0; cc < 3; ++cc) row[17 * (3 * r + cc)] = strict::mul(bb[r], a[cc]); }, c2);
+                sg = strict::mul(sg, one_over_n);            // lanes 0-8: covariance entry (lane / 3, lane % 3)
+                double sigma[3][3];
+#pragma unroll
+                for (int k = 0; k < 9; ++k) sigma[k / 3][k % 3] = __shfl_sync(0xffffffffu, sg, k);
+                stamp(22);   // strict: ordered sums done
                 if (lane == 0) strict::pose_from_sigma(sigma, ms, md, Um);
+                stamp(23);   // strict: Jacobi SVD + pose done
             }
             if (lane == 0) {
 #pragma unroll
@@ -527,15 +564,8 @@ icp_small2_kernel(const IcpParams p) {
                         s_tot[lane] = v;
                     }
                     __syncwarp();
-                    int ok = 1;
-                    if (!s_strict) {
-                        if (lane == 0) ok = fit_fast(!apply) ? 1 : 0;
-                        ok = __shfl_sync(0xffffffffu, ok, 0);
-                        if (!ok && lane == 0) s_strict = 1;   // first fit not certifiable: this tile follows the reference's arithmetic
-                    } else {
-                        ok = 0;
-                    }
-                    if (!ok) fit_strict();
+                    if (s_strict) fit_strict();
+                    else if (lane == 0) fit_fast();
                 }
             } else if (warp == 1) {
                 if (lane == 0) {

@@ -336,7 +336,10 @@ icp_tiles_kernel(const IcpParams p) {
     int rank = 0;                                        // CTA within the tile's cluster
     if constexpr (CS > 1) rank = (int)cg::this_cluster().block_rank();
     const int ns_tile = p.src_off[b + 1] - p.src_off[b];
-    const int per = (ns_tile + CS - 1) / CS;
+    // a tile whose box holds a handful of targets fits its poses in the reference's own arithmetic
+    // (icp_common.cuh, namespace strict); its sums run in ascending source index, so one CTA owns all of it
+    const bool strict_tile = p.cnt[b] <= p.strict_nt;
+    const int per = strict_tile ? ns_tile : (ns_tile + CS - 1) / CS;
     const int lo = min(ns_tile, rank * per);
     const int s0 = p.src_off[b] + lo;                    // this CTA's slice of the source points
     const int ns = min(ns_tile, lo + per) - lo;
@@ -668,6 +671,49 @@ icp_tiles_kernel(const IcpParams p) {
         for (int k = 0; k < 12; ++k) s_U[k] = Um[k];
     };
 
+    // strict pose fit (warp 0, all lanes): two-pass sums in ascending source index, one accumulator per lane,
+    // then the reference's Jacobi SVD on lane 0.  Targets of such a tile are resident (n_t <= strict_nt).
+    auto fit_strict = [&](int c) {
+        double Um[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
+        if (c > 0) {   // warp-uniform
+            const double *src1 = lane == 0 ? px : (lane == 1 ? py : (lane == 2 ? pz : (lane == 3 ? sqx : (lane == 4 ? sqy : sqz))));
+            double acc = 0.0;
+            if (lane < 6) {
+                for (int i = 0; i < ns; ++i) {
+                    const int j = cj[i];
+                    if (j >= 0) acc = strict::add(acc, src1[lane < 3 ? i : j]);
+                }
+            }
+            const double one_over_n = strict::dvd(1.0, (double)c);
+            const double mean = strict::mul(acc, one_over_n);   // lanes 0-2: source mean, 3-5: target mean
+            const int rr = lane < 9 ? lane / 3 : 0, cc = lane < 9 ? lane - 3 * rr : 0;
+            const double ms_c = __shfl_sync(0xffffffffu, mean, cc), md_r = __shfl_sync(0xffffffffu, mean, 3 + rr);
+            const double *pa = cc == 0 ? px : (cc == 1 ? py : pz);
+            const double *pb = rr == 0 ? sqx : (rr == 1 ? sqy : sqz);
+            double sg = 0.0;
+            if (lane < 9) {
+                for (int i = 0; i < ns; ++i) {
+                    const int j = cj[i];
+                    if (j >= 0) sg = strict::add(sg, strict::mul(strict::sub(pb[j], md_r), strict::sub(pa[i], ms_c)));
+                }
+                sg = strict::mul(sg, one_over_n);
+            }
+            double sigma[3][3], ms[3], md[3];
+#pragma unroll
+            for (int k = 0; k < 9; ++k) sigma[k / 3][k % 3] = __shfl_sync(0xffffffffu, sg, k);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                ms[k] = __shfl_sync(0xffffffffu, mean, k);
+                md[k] = __shfl_sync(0xffffffffu, mean, 3 + k);
+            }
+            if (lane == 0) strict::pose_from_sigma(sigma, ms, md, Um);
+        }
+        if (lane == 0) {
+#pragma unroll
+            for (int k = 0; k < 12; ++k) s_U[k] = Um[k];
+        }
+    };
+
     // T <- U * T, one lane per entry, entries summed left to right with each operation rounded
     auto compose_pose = [&]() {
         double v = 0.0;
@@ -689,7 +735,10 @@ icp_tiles_kernel(const IcpParams p) {
     if (rank == 0) {
         if (warp == 0) {
             const int c = CS > 1 ? cluster_totals(0) : totals(0);
-            if (lane == 0 && p.max_iter > 0) fit_pose(c);
+            if (p.max_iter > 0) {
+                if (strict_tile) fit_strict(c);
+                else if (lane == 0) fit_pose(c);
+            }
         } else if (warp == 1) {
             const int c = CS > 1 ? cluster_totals(1) : totals(1);
             if (lane == 0) {
@@ -714,7 +763,10 @@ icp_tiles_kernel(const IcpParams p) {
             if (warp == 0) {
                 // speculative: the fit for iteration it+1 runs while warp 1 decides whether to stop
                 const int c = CS > 1 ? cluster_totals(0) : totals(0);
-                if (lane == 0 && it + 1 < p.max_iter) fit_pose(c);
+                if (it + 1 < p.max_iter) {
+                    if (strict_tile) fit_strict(c);
+                    else if (lane == 0) fit_pose(c);
+                }
             } else if (warp == 1) {
                 const int c = CS > 1 ? cluster_totals(1) : totals(1);
                 if (lane == 0) {
@@ -808,7 +860,7 @@ static const Tuning &tuning() {
         v.small = geti("AURDF_ICP_SMALL", 2);
         v.minb = geti("AURDF_ICP_SMALL_MINB", 6);
         v.split = geti("AURDF_ICP_SMALL_SPLIT", 1);
-        v.strict_nt = geti("AURDF_ICP_STRICT_NT", 32);
+        v.strict_nt = geti("AURDF_ICP_STRICT_NT", 16);
         return v;
     }();
     return t;

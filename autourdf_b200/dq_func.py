@@ -3,9 +3,12 @@ with the same names, argument order, broadcasting batch dims and shape asserts, 
 one batched CUDA kernel (``aurdf_dq_op``).  Also the four pytorch3d 0.7.7 functions the
 reference imports (dq_func.py:2).  Real-first quaternions (w, x, y, z).
 
-Forward only: the reference differentiates through these only on the ``--r dq`` branch of
-train() (mlp_reg.py:78-84), which stays on torch autograd upstream and is out of this
-path's scope ("MLP optimisation loop").
+Differentiable: the reference backpropagates through ``matrix_to_quaternion`` /
+``quaternion_to_matrix`` (``--r q``, mlp_reg.py:60-66) and ``transform_to_dualquat`` /
+``dualquat_to_transform`` (``--r dq``, :78-84) between the pose MLP and ``loss.backward()``
+(:114-116).  Every operator here is a ``torch.autograd.Function`` whose backward is the CUDA
+vector-Jacobian kernel ``aurdf_dq_op_bwd`` (exact derivative of the same expression, on the branch
+the forward pass took -- the subgradient torch autograd uses for the reference's code).
 """
 from __future__ import annotations
 
@@ -18,9 +21,41 @@ _TORCH2DT = {torch.float32: _lib.F32, torch.float64: _lib.F64}
  _OP_P2DQ, _OP_QMUL, _OP_QINV, _OP_Q2M, _OP_M2Q) = range(15)
 
 
+class _DqOp(torch.autograd.Function):
+    """one batched operator of ``aurdf_dq_op``; inputs are contiguous and already broadcast"""
+
+    @staticmethod
+    def forward(ctx, op, n, out_shape, out1_shape, in0, in1):
+        L = _lib.lib()
+        out0 = torch.empty(out_shape, dtype=in0.dtype, device=in0.device)
+        out1 = torch.empty(out1_shape, dtype=in0.dtype, device=in0.device) if out1_shape is not None else None
+        _lib.check(L.aurdf_dq_op(op, _lib.ptr(in0), _lib.ptr(in1), _lib.ptr(out0), _lib.ptr(out1), n,
+                                 _TORCH2DT[in0.dtype], _lib.current_stream()), "aurdf_dq_op")
+        ctx.op, ctx.n = op, n
+        ctx.save_for_backward(in0, in1)
+        if out1 is None:
+            return out0
+        return out0, out1
+
+    @staticmethod
+    def backward(ctx, g0, g1=None):
+        L = _lib.lib()
+        in0, in1 = ctx.saved_tensors
+        need0, need1 = ctx.needs_input_grad[4], in1 is not None and ctx.needs_input_grad[5]
+        if not (need0 or need1):
+            return None, None, None, None, None, None
+        g0 = g0.contiguous() if g0 is not None else None
+        g1 = g1.contiguous() if g1 is not None else None
+        gin0 = torch.empty_like(in0) if need0 else None
+        gin1 = torch.empty_like(in1) if need1 else None
+        _lib.check(L.aurdf_dq_op_bwd(ctx.op, _lib.ptr(in0), _lib.ptr(in1), _lib.ptr(g0), _lib.ptr(g1), _lib.ptr(gin0),
+                                     _lib.ptr(gin1), ctx.n, _TORCH2DT[in0.dtype], _lib.current_stream()), "aurdf_dq_op_bwd")
+        return None, None, None, None, gin0, gin1
+
+
 def _run(op, in0, in_tail, in1, in1_tail, out_tail, out1_tail=None):
-    """flatten batch dims, launch, reshape; *_tail = trailing element shape of each operand"""
-    L = _lib.lib()
+    """flatten batch dims, launch, reshape; *_tail = trailing element shape of each operand.
+    Broadcasting / dtype conversion happen in torch (differentiable), the operator itself in CUDA."""
     assert in0.is_cuda and in0.dtype in _TORCH2DT, "dq_func operators need CUDA float32/float64 tensors"
     batch = in0.shape[:len(in0.shape) - len(in_tail)]
     if in1 is not None:
@@ -34,11 +69,8 @@ def _run(op, in0, in_tail, in1, in1_tail, out_tail, out1_tail=None):
     n = 1
     for d in batch:
         n *= int(d)
-    out0 = torch.empty(tuple(batch) + tuple(out_tail), dtype=in0.dtype, device=in0.device)
-    out1 = torch.empty(tuple(batch) + tuple(out1_tail), dtype=in0.dtype, device=in0.device) if out1_tail else None
-    _lib.check(L.aurdf_dq_op(op, _lib.ptr(in0), _lib.ptr(in1), _lib.ptr(out0), _lib.ptr(out1), n,
-                             _TORCH2DT[in0.dtype], _lib.current_stream()), "aurdf_dq_op")
-    return (out0, out1) if out1_tail else out0
+    return _DqOp.apply(op, n, tuple(batch) + tuple(out_tail), tuple(batch) + tuple(out1_tail) if out1_tail else None,
+                       in0, in1)
 
 
 # ---- pytorch3d.transforms (dq_func.py:2) -------------------------------------------------

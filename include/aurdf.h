@@ -219,6 +219,13 @@ enum {
  * has two).  Contiguous, batch-major. */
 AURDF_API int aurdf_dq_op(int op, const void *in0, const void *in1, void *out0, void *out1, int64_t n,
                 int dtype, aurdf_stream_t stream);
+/* Vector-Jacobian product of the same operator (what loss.backward() needs at
+ * PointCloud/mlp_reg.py:114-116 when train() runs with --r q / --r dq, :60-84):
+ * gin_k = sum_m gout_m * d out_m / d in_k, evaluated on the branch the forward pass took.
+ * gout0/gout1: gradients w.r.t. out0/out1 (either may be NULL = zero); gin0/gin1: gradients
+ * w.r.t. in0/in1 (either may be NULL = not wanted; gin1 is ignored for unary ops). */
+AURDF_API int aurdf_dq_op_bwd(int op, const void *in0, const void *in1, const void *gout0, const void *gout1,
+                    void *gin0, void *gin1, int64_t n, int dtype, aurdf_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------
  * Pairwise cluster motion-distance map: replaces CoordMap.coord_dist_map,

@@ -10,8 +10,8 @@ d = ci.batch_to_device(b)
 r = ci.icp_sweep(d["src"], d["src_off"], d["tgt"], d["tgt_off"], d["tile_frame"], d["box"], d["box_off"], d["init_T"],
                  max_src_per_tile=int(np.diff(b.src_off).max()))
 iters = r.iters.cpu().numpy(); ntgt = r.ntgt.cpu().numpy()
-t = int(iters.argmax())
-print("longest tile", t, "iters", iters[t], "ns", b.src_off[t+1]-b.src_off[t], "nt", ntgt[t])
+t = int(os.environ.get("AURDF_TILE", iters.argmax()))
+print("tile", t, "iters", iters[t], "ns", b.src_off[t+1]-b.src_off[t], "nt", ntgt[t])
 
 def single(t):
     f = int(b.tile_frame[t])
@@ -63,7 +63,8 @@ if os.environ.get("AURDF_ICP_SMALL", "128") != "0":
     if os.environ.get("AURDF_ICP_SMALL", "2") == "2":   # icp_small2_kernel
         ids = {0: "iteration start", 1: "P update", 2: "cache test", 3: "float32 scan (misses)", 4: "merge+certificate+exact distance",
                5: "pass end", 7: "moment reduction", 8: "barrier A", 20: "totals+covariance", 21: "rotation fit",
-               9: "translation+store U (fit done)"}
+               9: "translation+store U (fit done)", 22: "strict: ordered sums", 23: "strict: Jacobi SVD + pose",
+               30: "reduce: loads issued", 31: "reduce: products done"}
     c = c.reshape(-1, 2)
     c = c[c[:, 0] > 0]
     from collections import OrderedDict

@@ -93,47 +93,8 @@ def _install_open3d():
 
 # ------------------------------------------------------------------ pytorch3d stand-in
 def _install_pytorch3d():
-    def quaternion_raw_multiply(a, b):
-        aw, ax, ay, az = torch.unbind(a, -1)
-        bw, bx, by, bz = torch.unbind(b, -1)
-        ow = aw * bw - ax * bx - ay * by - az * bz
-        ox = aw * bx + ax * bw + ay * bz - az * by
-        oy = aw * by - ax * bz + ay * bw + az * bx
-        oz = aw * bz + ax * by - ay * bx + az * bw
-        return torch.stack((ow, ox, oy, oz), -1)
-
-    def quaternion_invert(q):
-        return q * q.new_tensor([1, -1, -1, -1])
-
-    def quaternion_to_matrix(q):
-        r, i, j, k = torch.unbind(q, -1)
-        two_s = 2.0 / (q * q).sum(-1)
-        o = torch.stack((1 - two_s * (j * j + k * k), two_s * (i * j - k * r), two_s * (i * k + j * r),
-                         two_s * (i * j + k * r), 1 - two_s * (i * i + k * k), two_s * (j * k - i * r),
-                         two_s * (i * k - j * r), two_s * (j * k + i * r), 1 - two_s * (i * i + j * j)), -1)
-        return o.reshape(q.shape[:-1] + (3, 3))
-
-    def _sqrt_positive_part(x):
-        ret = torch.zeros_like(x)
-        pos = x > 0
-        ret[pos] = torch.sqrt(x[pos])
-        return ret
-
-    def matrix_to_quaternion(matrix):
-        batch = matrix.shape[:-2]
-        m00, m01, m02, m10, m11, m12, m20, m21, m22 = torch.unbind(matrix.reshape(batch + (9,)), dim=-1)
-        q_abs = _sqrt_positive_part(torch.stack([1.0 + m00 + m11 + m22, 1.0 + m00 - m11 - m22,
-                                                 1.0 - m00 + m11 - m22, 1.0 - m00 - m11 + m22], dim=-1))
-        quat_by_rijk = torch.stack([
-            torch.stack([q_abs[..., 0] ** 2, m21 - m12, m02 - m20, m10 - m01], dim=-1),
-            torch.stack([m21 - m12, q_abs[..., 1] ** 2, m10 + m01, m02 + m20], dim=-1),
-            torch.stack([m02 - m20, m10 + m01, q_abs[..., 2] ** 2, m12 + m21], dim=-1),
-            torch.stack([m10 - m01, m20 + m02, m21 + m12, q_abs[..., 3] ** 2], dim=-1)], dim=-2)
-        flr = torch.tensor(0.1).to(dtype=q_abs.dtype, device=q_abs.device)
-        cand = quat_by_rijk / (2.0 * q_abs[..., None].max(flr))
-        idx = q_abs.argmax(dim=-1)
-        out = torch.gather(cand, -2, idx[..., None, None].expand(batch + (1, 4)))[..., 0, :]
-        return torch.where(out[..., 0:1] < 0, -out, out)
+    from oracle.pt3d_torch import (matrix_to_quaternion, quaternion_invert, quaternion_raw_multiply,  # noqa: F401
+                                   quaternion_to_matrix)
 
     p3d = types.ModuleType("pytorch3d")
     tr = types.ModuleType("pytorch3d.transforms")

@@ -21,21 +21,23 @@ def cuda_sweep(b, pts_dtype=None, **kw):
 def ill_posed_tiles(b, o, rel=1e-6):
     """Tiles in which some Kabsch fit of the ICP run had a rank<=1 covariance (the oracle reports
     cond = min over iterations of sigma_2/sigma_1): fewer than 3 non-collinear matched points.
-    There the optimal rotation is a one-parameter family (free spin about the line); open3d/Eigen,
-    the oracle and the GPU each return one member and the runs diverge from that iteration on, so
-    these tiles are compared on mask counts and validity only.  They arise when an inflated box
-    holds 1-3 target points (thin clusters)."""
+    There the optimal rotation is a one-parameter family (free spin about the line) and the member
+    an SVD returns is decided by its own rounding.  They arise when an inflated box holds 1-3 target
+    points (thin clusters).  The CUDA kernels fit such tiles in "strict" mode -- the oracle's
+    arithmetic operation for operation -- so they are compared like every other tile; this helper
+    only reports how many there are."""
     return np.nonzero(o["cond"] <= rel)[0]
 
 
-def assert_parity(g, o, pose_tol=1e-5, what="", batch=None):
+def assert_parity(g, o, pose_tol=1e-5, what="", batch=None, exclude_ill_posed=False):
     """bit-exact correspondence indices, masked counts and iteration counts; poses within 1e-5
-    (north_star tolerance); world points within 1e-5.  With ``batch`` given, rank-deficient
-    tiles (see ill_posed_tiles) are excluded from the pose comparison and must stay rare."""
+    (north_star tolerance); world points within 1e-5 -- on EVERY tile.  (``exclude_ill_posed`` is the
+    round-1 behaviour, kept for A/B runs of the older kernels only: rank-deficient tiles are then
+    left out of the pose comparison.)"""
     assert np.array_equal(g["ntgt"], o["ntgt"]), f"{what}: masked target counts differ"
     keep = np.ones(o["T"].shape[0], dtype=bool)
     pkeep = np.ones(o["world"].shape[0], dtype=bool)
-    if batch is not None:
+    if batch is not None and exclude_ill_posed:
         ill = ill_posed_tiles(batch, o)
         assert ill.size <= max(1, 0.02 * batch.n_tiles), f"{what}: {ill.size} ill-posed tiles"
         keep[ill] = False

@@ -35,8 +35,21 @@ def test_franka_c3_parity(oracle, synth):
 
 
 def test_allegro_c4_parity(oracle, synth):
-    b = synth.make_config("allegro_hand", n_seq=2)
-    assert_parity(cuda_sweep(b), oracle_sweep(oracle, b, use_kdtree=True), what="allegro", batch=b)
+    """the full C4 config (5 sequences, 2160 tiles), rank-deficient tiles included"""
+    b = synth.make_config("allegro_hand")
+    o = oracle_sweep(oracle, b, use_kdtree=True)
+    assert_parity(cuda_sweep(b), o, what="allegro", batch=b)
+    assert (o["cond"] <= 1e-6).sum() >= 10, "config is expected to contain rank-deficient tiles"
+
+
+@pytest.mark.parametrize("n_points,n_clusters,n_frames", [(1024, 8, 11), (4096, 32, 11), (16384, 32, 6), (16384, 128, 6),
+                                                          (65536, 128, 6), (65536, 8, 4)])
+def test_c5_sweep_points_parity(oracle, synth, n_points, n_clusters, n_frames):
+    """points of the C5 sweep (BASELINE.json configs[4]): small tiles, 512-point tiles (general kernel),
+    8192-point tiles (thread-block-cluster variant)"""
+    oracle.use_all_host_threads()
+    b = synth.make_batch(n_points=n_points, n_clusters=n_clusters, n_seq=1, n_frames=n_frames, dof=5, cid=5)
+    assert_parity(cuda_sweep(b), oracle_sweep(oracle, b, use_kdtree=True), what=f"C5 {n_points}x{n_clusters}", batch=b)
 
 
 def test_f32_storage_same_result(oracle, synth):

@@ -284,3 +284,91 @@ def test_newton_pose_fit_equals_umeyama_or_declines(oracle):
     assert _newton4(mirror) is None
     rank1 = np.outer([1.0, 2.0, 3.0], [0.5, -1.0, 2.0]) * 1e-5     # collinear matches
     assert _newton4(rank1) is None
+
+
+# ------------------------------------------------------------------ icp_small2_kernel: nearest-neighbour cache
+def _cache_state(P, Q):
+    """what a scan of icp_small2_kernel leaves per point: winner j1, anchor (float32 about Q[0]), and
+    rho = lower bound on the distance from the anchor position to every other target (0 = no bound)"""
+    keys, aq, f32 = _f32_keys(P, Q)
+    nt = Q.shape[0]
+    order = np.sort(keys, axis=1)
+    m1 = order[:, 0]
+    m2 = order[:, 1] if nt > 1 else np.full_like(m1, 0xFFFFFFFF)
+    j1 = (m1 & IDX_MASK).astype(np.int64)
+    m1hi = (m1 | IDX_MASK).view(np.float32)
+    m2lo = (m2 & ~IDX_MASK).view(np.float32)
+    m2hi = (m2 | IDX_MASK).view(np.float32)
+    amag = np.maximum(aq, np.abs(f32).max(axis=1)).astype(np.float32)
+    dl = np.float32(4.0) * U32 * amag
+    with np.errstate(invalid="ignore", over="ignore"):
+        tau = np.float32(16.0) * (dl * np.sqrt(m2hi) * np.float32(1.001) + dl * dl + U32 * m2hi)
+        cert = (m2lo - m1hi > np.float32(2.0) * tau) & (m2hi < np.inf)
+        rho = np.where((m2lo > np.float32(128.0) * dl * dl) & (m2lo - tau > 0),
+                       np.sqrt(np.maximum(m2lo - tau, np.float32(0))) * np.float32(0.9999), np.float32(0)).astype(np.float32)
+    if nt == 1:
+        cert = np.ones_like(cert)
+        rho = np.full_like(rho, 1e30)
+    rho = np.where(cert, rho, np.float32(0))          # an uncertified point keeps no bound
+    return j1, f32, rho, aq
+
+
+def _cache_hit(Pnew, Q, j1, anchor32, rho, aq):
+    """the kernel's cache test for points that moved to Pnew (float32 arithmetic as written there)"""
+    o = Q[0]
+    f = (Pnew - o).astype(np.float32)
+    d = Pnew - Q[j1]
+    D1 = (d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]) + d[:, 2] * d[:, 2]
+    e = f - anchor32
+    ex, ey, ez = (e[:, k].astype(np.float64) for k in range(3))
+    s = (ex * ex).astype(np.float32)
+    s = (ey * ey + s.astype(np.float64)).astype(np.float32)
+    s = (ez * ez + s.astype(np.float64)).astype(np.float32)
+    dele = np.sqrt(s)
+    amag = np.maximum(aq, np.abs(f).max(axis=1)).astype(np.float32)
+    lhs = (np.sqrt(D1.astype(np.float32)) + dele) * np.float32(1.0001) + np.float32(1e-6) * (amag + dele)
+    return (rho > 0) & (lhs < rho)
+
+
+@pytest.mark.parametrize("kind", ["random", "bisector", "duplicates"])
+def test_nn_cache_certificate_is_sound(kind):
+    """whenever the cache test of icp_small2_kernel keeps the previous winner after a move, that winner
+    is the float64 argmin at the new position (reference operation order, lowest index on ties)"""
+    rng = np.random.default_rng({"random": 11, "bisector": 12, "duplicates": 13}[kind])
+    checked = hits = 0
+    for trial in range(120):
+        nt = int(rng.choice([1, 2, 3, 17, 64, 131, 300, 760]))
+        P, Q = _tile(rng, kind, nt, 192)
+        j1, anchor32, rho, aq = _cache_state(P, Q)
+        ext = np.abs(Q - Q[0]).max() + 1e-6
+        for scale in (1e-7, 1e-5, 1e-3, 3e-2, 0.3):      # moves from far below to far above the target spacing
+            step = rng.normal(size=P.shape) * (scale * ext)
+            if kind != "random":                          # move straight at a rival target now and then
+                rival = Q[rng.integers(0, nt, P.shape[0])]
+                step = np.where(rng.random((P.shape[0], 1)) < 0.5, (rival - P) * rng.uniform(0, 1.2, (P.shape[0], 1)), step)
+            Pn = P + step
+            hit = _cache_hit(Pn, Q, j1, anchor32, rho, aq)
+            ex = _exact_argmin(Pn, Q)
+            wrong = hit & (j1 != ex)
+            assert not wrong.any(), f"{kind}: cache kept a wrong neighbour (trial {trial}, n_t {nt}, move {scale})"
+            checked += hit.size
+            hits += int(hit.sum())
+    assert hits / checked > (0.25 if kind == "random" else 0.05), f"cache useless: {hits / checked:.3f}"
+
+
+def test_small2_home_slot_mapping_is_a_bijection():
+    """icp_small2_kernel deals the source points round-robin to its four warps: slot <-> point"""
+    s2p = lambda t: (t & ~127) + 4 * (t & 31) + ((t >> 5) & 3)
+    p2s = lambda i: (i & ~127) + 32 * (i & 3) + ((i & 127) >> 2)
+    for n in (128, 256):
+        assert sorted(s2p(t) for t in range(n)) == list(range(n))
+        assert all(p2s(s2p(t)) == t for t in range(n))
+    for ns in (1, 5, 20, 113, 128, 129, 200, 256):     # every warp's home points fill its first lanes
+        for r in range((ns + 127) // 128):
+            for w in range(4):
+                act = [128 * r + 4 * l + w < ns for l in range(32)]
+                k = sum(act)
+                assert act == [True] * k + [False] * (32 - k)
+                left = ns - 128 * r - w
+                assert k == (0 if left <= 0 else min(32, (left + 3) >> 2))
+                assert (0 if left <= 0 else min(8, (left + 15) >> 4)) == (k + 3) // 4

@@ -194,3 +194,68 @@ def test_resample_cluster_vs_oracle_and_sklearn():
     assert all(np.array_equal(a, b_) for a, b_ in zip(got, got2))
     with pytest.raises(NotImplementedError):
         resample_cluster(cloud, 0, K, mats, normal=True)
+
+
+def _rand_dq_inputs(n, dt, seed=0):
+    from scipy.spatial.transform import Rotation
+    g = torch.Generator().manual_seed(seed)
+    R = torch.tensor(Rotation.random(n, random_state=seed).as_matrix(), dtype=dt)
+    t = torch.randn(n, 3, generator=g, dtype=dt)
+    T = torch.eye(4, dtype=dt).repeat(n, 1, 1)
+    T[:, :3, :3], T[:, :3, 3] = R, t
+    q = torch.randn(n, 4, generator=g, dtype=dt)
+    dq = torch.randn(n, 8, generator=g, dtype=dt)
+    return dict(R=R, t=t, T=T, q=q, q2=torch.randn(n, 4, generator=g, dtype=dt), dq=dq,
+                dq2=torch.randn(n, 8, generator=g, dtype=dt), p=torch.randn(n, 3, generator=g, dtype=dt))
+
+
+def test_dq_func_backward_matches_finite_differences():
+    """every operator of aurdf_dq_op_bwd against torch.autograd.gradcheck (float64, central differences)"""
+    from autourdf_b200 import dq_func as D
+    x = {k: v.cuda() for k, v in _rand_dq_inputs(6, torch.float64, seed=3).items()}
+    r = lambda a: a.clone().requires_grad_(True)
+    cases = [(D.transform_from_rot_trans, (x["R"], x["t"])), (D.quaternion_conjugate, (x["q"],)),
+             (D.quat_trans_to_dualquat, (x["q"], x["t"])), (D.rot_trans_to_dualquat, (x["R"], x["t"])),
+             (D.transform_to_dualquat, (x["T"],)), (D.dualquat_to_quat_trans, (x["dq"],)),
+             (D.dualquat_to_rot_trans, (x["dq"],)), (D.dualquat_to_transform, (x["dq"],)),
+             (D.dualquat_multiply, (x["dq"], x["dq2"])), (D.dualquat_invert, (x["dq"],)), (D.point_to_dualquat, (x["p"],)),
+             (D.quaternion_raw_multiply, (x["q"], x["q2"])), (D.quaternion_invert, (x["q"],)),
+             (D.quaternion_to_matrix, (x["q"],)), (D.matrix_to_quaternion, (x["R"],))]
+    for fn, args in cases:
+        assert torch.autograd.gradcheck(fn, tuple(r(a) for a in args), eps=1e-6, atol=1e-6, rtol=1e-5), fn.__name__
+
+
+@pytest.mark.parametrize("dt", [torch.float32, torch.float64])
+def test_dq_func_backward_matches_torch_autograd_of_the_reference_expressions(dt):
+    """the two pairs train() differentiates through (mlp_reg.py:60-66 `--r q`, :78-84 `--r dq`): gradients of
+    the CUDA operators vs torch autograd through the restated reference expressions, incl. broadcasting"""
+    from autourdf_b200 import dq_func as D
+    from oracle import pt3d_torch as P
+    x = {k: v.cuda() for k, v in _rand_dq_inputs(48, dt, seed=7).items()}
+    x["R"][1] = torch.diag(torch.tensor([1.0, -1.0, -1.0], dtype=dt)).cuda()      # other arg-max branches
+    x["R"][2] = torch.diag(torch.tensor([-1.0, 1.0, -1.0], dtype=dt)).cuda()
+    x["T"][1, :3, :3], x["T"][2, :3, :3] = x["R"][1], x["R"][2]
+    tol = 2e-4 if dt == torch.float32 else 1e-10
+    pairs = [(D.matrix_to_quaternion, P.matrix_to_quaternion, "R"), (D.quaternion_to_matrix, P.quaternion_to_matrix, "q"),
+             (D.transform_to_dualquat, P.transform_to_dualquat, "T"), (D.dualquat_to_transform, P.dualquat_to_transform, "dq")]
+    for ours, ref, key in pairs:
+        a, b = x[key].clone().requires_grad_(True), x[key].clone().requires_grad_(True)
+        ya, yb = ours(a), ref(b)
+        w = torch.randn_like(yb)
+        assert (ya - yb).abs().max().item() <= tol, ours.__name__
+        (ya * w).sum().backward()
+        (yb * w).sum().backward()
+        scale = max(1.0, b.grad.abs().max().item())
+        assert (a.grad - b.grad).abs().max().item() <= tol * scale, f"{ours.__name__}: gradient differs"
+    # the composition of the `--r dq` branch with a parameter in between, and a broadcast operand
+    w8 = torch.randn(8, dtype=dt, device="cuda", requires_grad=True)
+    T = D.dualquat_to_transform(D.transform_to_dualquat(x["T"]) * w8)
+    T.square().sum().backward()
+    w8r = w8.detach().clone().requires_grad_(True)
+    P.dualquat_to_transform(P.transform_to_dualquat(x["T"]) * w8r).square().sum().backward()
+    assert (w8.grad - w8r.grad).abs().max().item() <= tol * max(1.0, w8r.grad.abs().max().item()) * 10
+    qa = x["q"][:1].clone().requires_grad_(True)                                  # (1,4) broadcast against (48,4)
+    D.quaternion_raw_multiply(qa, x["q2"]).sum().backward()
+    qb = x["q"][:1].clone().requires_grad_(True)
+    P.quaternion_raw_multiply(qb, x["q2"]).sum().backward()
+    assert (qa.grad - qb.grad).abs().max().item() <= tol * 50
