@@ -152,8 +152,11 @@ class HostSweep:
         return a.value, b.value
 
     def run(self, src, src_off, tgt, tgt_off, tile_frame, box, box_off, init_T, box_scale=1.2, max_corr=1.0,
-            max_iter=10000, rel_fitness=1e-6, rel_rmse=1e-6, ori_only=False, out=None):
-        """All arguments are C-contiguous numpy arrays in the C-ABI layout (box may be None)."""
+            max_iter=10000, rel_fitness=1e-6, rel_rmse=1e-6, ori_only=False, out=None, want_world=True,
+            want_corr=True):
+        """All arguments are C-contiguous numpy arrays in the C-ABI layout (box may be None).
+        ``want_world`` / ``want_corr`` = False leaves the per-point outputs on the device (``out["world"]`` /
+        ``out["corr"]`` are then None): a caller that only needs the fitted poses moves 85 % fewer bytes back."""
         assert src.dtype == tgt.dtype and src.dtype in (np.float32, np.float64)
         assert init_T.dtype == np.float64 and src_off.dtype == np.int32 and tgt_off.dtype == np.int32
         assert tile_frame.dtype == np.int32 and (box is None or box_off.dtype == np.int32)
@@ -161,7 +164,8 @@ class HostSweep:
             assert a is None or a.flags.c_contiguous
         B, F, N = int(tile_frame.shape[0]), int(tgt_off.shape[0]) - 1, int(src.shape[0])
         if out is None:
-            out = dict(T=np.empty((B, 4, 4)), world=np.empty((N, 3)), corr=np.empty(N, dtype=np.int32),
+            out = dict(T=np.empty((B, 4, 4)), world=np.empty((N, 3)) if want_world else None,
+                       corr=np.empty(N, dtype=np.int32) if want_corr else None,
                        fitness=np.empty(B), rmse=np.empty(B), iters=np.empty(B, dtype=np.int32),
                        ntgt=np.empty(B, dtype=np.int32))
         dt = lambda a: _lib.F32 if a.dtype == np.float32 else _lib.F64
@@ -169,7 +173,8 @@ class HostSweep:
             self._h, _lib.ptr(src), dt(src), _lib.ptr(src_off), _lib.ptr(tgt), _lib.ptr(tgt_off),
             _lib.ptr(tile_frame), _lib.ptr(box), _lib.F64 if box is None else dt(box), _lib.ptr(box_off),
             _lib.ptr(init_T), B, F, float(box_scale), float(max_corr), int(max_iter), float(rel_fitness),
-            float(rel_rmse), int(bool(ori_only)), _lib.ptr(out["T"]), _lib.ptr(out["world"]), _lib.ptr(out["corr"]),
+            float(rel_rmse), int(bool(ori_only)), _lib.ptr(out["T"]), _lib.ptr(out["world"] if want_world else None),
+            _lib.ptr(out["corr"] if want_corr else None),
             _lib.ptr(out["fitness"]), _lib.ptr(out["rmse"]), _lib.ptr(out["iters"]), _lib.ptr(out["ntgt"]))
         _lib.check(rc, "aurdf_icp_sweep_host")
         return out
@@ -213,7 +218,8 @@ def masked_icp(clusters_local, clusters_world, step_pc_np, matrices, visual=Fals
     else:
         init = np.ascontiguousarray(np.asarray([np.asarray(m, dtype=np.float64) for m in matrices[:K]]).reshape(K, 4, 4))
     r = _host_ctx().run(src, src_off, tgt, np.array([0, tgt.shape[0]], dtype=np.int32), np.zeros(K, dtype=np.int32),
-                        box, box_off, init, box_scale=scale, max_corr=th, max_iter=10000, ori_only=ori)
+                        box, box_off, init, box_scale=scale, max_corr=th, max_iter=10000, ori_only=ori,
+                        want_corr=_details is not None)
     if _details is not None:
         _details.update(r, src_off=src_off)
     # the output buffer is freshly allocated by run(): the per-cluster views own it, no copy needed
@@ -243,7 +249,7 @@ def registration_icp(source, target, max_correspondence_distance, init=None, max
     r = _host_ctx().run(src, np.array([0, src.shape[0]], dtype=np.int32), tgt,
                         np.array([0, tgt.shape[0]], dtype=np.int32), np.zeros(1, dtype=np.int32), None, None,
                         init.reshape(1, 4, 4), box_scale=1.0, max_corr=max_correspondence_distance,
-                        max_iter=max_iteration, rel_fitness=relative_fitness, rel_rmse=relative_rmse)
+                        max_iter=max_iteration, rel_fitness=relative_fitness, rel_rmse=relative_rmse, want_world=False)
     corr = r["corr"]
     i = np.nonzero(corr >= 0)[0]
     return RegistrationResult(r["T"][0], float(r["fitness"][0]), float(r["rmse"][0]),

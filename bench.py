@@ -140,8 +140,9 @@ def config_dict(b, name, scaling, world):
                             f"every GPU sweeps its own {name} sequences ({world} GPU(s))") + ", one all-gather of poses"}
 
 
-def finish(world):
-    """bounded exit: the JSON line is out; tear the process group down under a watchdog and leave"""
+def finish(world, line=None):
+    """bounded exit: tear the process group down under a watchdog, THEN print the JSON line (rank 0), so it is
+    the last line on stdout even when NCCL_DEBUG=INFO logs the communicator teardown, and leave"""
     sys.stdout.flush()
     sys.stderr.flush()
     if world > 1:
@@ -149,6 +150,11 @@ def finish(world):
         t = threading.Thread(target=dist.destroy_process_group, daemon=True)
         t.start()
         t.join(20.0)
+        if line is not None:
+            time.sleep(0.5)          # let the other ranks' teardown lines through first
+    if line is not None:
+        print(line, flush=True)
+    sys.stderr.flush()
     os._exit(0)
 
 
@@ -469,7 +475,7 @@ def main():
                    "modes_frames_per_s": {k: m["value"] for k, m in modes.items()},
                    "all_core_port_frames_per_s": modes["tile_parallel"]["value"],
                    "host_threads": O.lib().orc_max_threads()}
-        print(json.dumps({
+        line = json.dumps({
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True,
             "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -482,9 +488,9 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": int(L.aurdf_icp_sweep_launches()) * args.steps,
             "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
-        }), flush=True)
+        })
     host.close()
-    finish(world)
+    finish(world, line if rank == 0 else None)
 
 
 if __name__ == "__main__":
