@@ -37,6 +37,10 @@ SIGNATURES = {
     "aurdf_nn_f32_workspace_bytes": (_sz, [_i64]),
     "aurdf_nn_f32": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i64, _i64, C.c_int, _vp, _vp, _vp, _sz, _vp]),
     "aurdf_nn_f32_bwd": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i64, C.c_int, _vp, _vp, _vp]),
+    "aurdf_chamfer_workspace_bytes": (_sz, [_i32, _i32, _i32]),
+    "aurdf_chamfer_workspace_init": (C.c_int, [_vp, _sz, _vp]),
+    "aurdf_chamfer_fwd": (C.c_int, [_vp, _vp, _i32, _i32, _i32, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "aurdf_chamfer_bwd": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp]),
     "aurdf_se3_apply": (C.c_int, [_vp, _vp, _vp, _i32, _i64, C.c_int, _vp, _vp]),
     "aurdf_se3_apply_bwd": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i64, C.c_int, _vp, _vp, _vp]),
     "aurdf_se3_to_local": (C.c_int, [_vp, _vp, _vp, _i32, _i64, _vp, _vp]),

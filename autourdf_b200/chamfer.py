@@ -2,9 +2,10 @@
 uses it (``chamfer_distance(pred, y, norm=1)``, PointCloud/mlp_reg.py:96 inside the 300-epoch
 ``train`` loop, and Sim/evaluation.py:81) -- SURVEY.md section 8(f)-1.
 
-Both nearest-neighbour directions run on the float32 brute-force kernel ``aurdf_nn_f32`` (split
-over query blocks AND target slices, merged by a packed 64-bit atomicMin); the backward is
-pytorch3d's ``knn_points`` backward (``aurdf_nn_f32_bwd``).  Differentiable in ``x`` and ``y``.
+``chamfer_distance`` is one fused launch (``aurdf_chamfer_fwd``: both nearest-neighbour directions, split over
+query blocks AND target slices, merged by the last-arriving CTA, reductions and the scalar loss in the same
+kernel) and one more for the backward (``aurdf_chamfer_bwd``, pytorch3d's ``knn_points`` backward for both
+directions).  ``knn1`` is the stand-alone packed 1-NN (``aurdf_nn_f32``).  Differentiable in ``x`` and ``y``.
 Supported subset of pytorch3d's signature: ``norm`` 1 or 2, ``batch_reduction`` / ``point_reduction``
 in {"mean", "sum"}, optional lengths; normals / weights / single_directional are not used by the
 reference and raise NotImplementedError.
@@ -63,6 +64,56 @@ class _Knn1(torch.autograd.Function):
         return g1, None, g2, None, None
 
 
+_WS = {}   # (device index, N, P1, P2) -> workspace tensor, initialised once (self-resetting arrival counters)
+
+
+def _workspace(dev, N, P1, P2):
+    key = (dev.index, N, P1, P2, torch.cuda.current_stream(dev).cuda_stream)
+    ws = _WS.get(key)
+    if ws is None:
+        L = _lib.lib()
+        ws = torch.empty(max(L.aurdf_chamfer_workspace_bytes(N, P1, P2), 256), dtype=torch.uint8, device=dev)
+        _lib.check(L.aurdf_chamfer_workspace_init(_lib.ptr(ws), ws.numel(), _lib.current_stream()), "aurdf_chamfer_workspace_init")
+        if len(_WS) > 64:
+            _WS.clear()
+        _WS[key] = ws
+    return ws
+
+
+class _Chamfer(torch.autograd.Function):
+    """loss = chamfer_distance(x, y): one forward launch, one backward launch"""
+
+    @staticmethod
+    def forward(ctx, x, y, norm, point_mean, batch_mean):
+        L = _lib.lib()
+        N, P1, P2 = x.shape[0], x.shape[1], y.shape[1]
+        ws = _workspace(x.device, N, P1, P2)
+        idx = torch.empty(N * (P1 + P2), dtype=torch.int32, device=x.device)
+        loss = torch.empty((), dtype=torch.float32, device=x.device)
+        _lib.check(L.aurdf_chamfer_fwd(x.data_ptr(), y.data_ptr(), N, P1, P2, norm, point_mean, batch_mean, idx.data_ptr(),
+                                       idx.data_ptr() + 4 * N * P1, loss.data_ptr(), ws.data_ptr(), ws.numel(),
+                                       _lib.current_stream()), "aurdf_chamfer_fwd")
+        ctx.save_for_backward(x, y, idx)
+        ctx.cfg = (norm, point_mean, batch_mean)
+        return loss
+
+    @staticmethod
+    def backward(ctx, gloss):
+        x, y, idx = ctx.saved_tensors
+        norm, point_mean, batch_mean = ctx.cfg
+        L = _lib.lib()
+        N, P1, P2 = x.shape[0], x.shape[1], y.shape[1]
+        need_x, need_y = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        g = torch.zeros(N * ((P1 if need_x else 0) + (P2 if need_y else 0)) * 3, dtype=torch.float32, device=x.device)
+        gx = g[:N * P1 * 3].view(N, P1, 3) if need_x else None
+        gy = g[(N * P1 * 3 if need_x else 0):].view(N, P2, 3) if need_y else None
+        gloss = gloss.contiguous().to(torch.float32)
+        _lib.check(L.aurdf_chamfer_bwd(x.data_ptr(), y.data_ptr(), idx.data_ptr(), idx.data_ptr() + 4 * N * P1,
+                                       gloss.data_ptr(), N, P1, P2, norm, point_mean, batch_mean, _lib.ptr(gx), _lib.ptr(gy),
+                                       _lib.current_stream()), "aurdf_chamfer_bwd")
+        return gx, gy, None, None, None
+
+
 def chamfer_distance(x, y, x_lengths=None, y_lengths=None, x_normals=None, y_normals=None, weights=None,
                      batch_reduction="mean", point_reduction="mean", norm: int = 2, single_directional=False,
                      abs_cosine=True):
@@ -74,21 +125,12 @@ def chamfer_distance(x, y, x_lengths=None, y_lengths=None, x_normals=None, y_nor
     if batch_reduction not in ("mean", "sum") or point_reduction not in ("mean", "sum"):
         raise NotImplementedError("reductions other than mean / sum")
     assert x.dim() == 3 and y.dim() == 3 and x.shape[0] == y.shape[0] and x.shape[2] == 3 and y.shape[2] == 3
-    N, P1, P2 = x.shape[0], x.shape[1], y.shape[1]
     if x_lengths is not None or y_lengths is not None:
         raise NotImplementedError("ragged batches: use knn1 with explicit offsets")
-    xo, _ = _offsets(None, P1, N, x.device)
-    yo, _ = _offsets(None, P2, N, x.device)
-    xf = x.reshape(N * P1, 3).to(torch.float32)
-    yf = y.reshape(N * P2, 3).to(torch.float32)
-    dx, _ = _Knn1.apply(xf, xo, yf, yo, norm)
-    dy, _ = _Knn1.apply(yf, yo, xf, xo, norm)
-    cham_x = dx.reshape(N, P1).sum(1)
-    cham_y = dy.reshape(N, P2).sum(1)
-    if point_reduction == "mean":
-        cham_x = cham_x / max(P1, 1)
-        cham_y = cham_y / max(P2, 1)
-    cham_x, cham_y = cham_x.sum(), cham_y.sum()
-    if batch_reduction == "mean":
-        cham_x, cham_y = cham_x / max(N, 1), cham_y / max(N, 1)
-    return cham_x + cham_y, None
+    if not x.is_cuda:
+        raise _lib.AurdfError("chamfer_distance: CUDA tensors only (there is no CPU fallback)")
+    if x.shape[0] == 0 or x.shape[1] == 0 or y.shape[1] == 0:
+        raise ValueError("chamfer_distance: empty batch or cloud")
+    xf = x.to(torch.float32).contiguous()
+    yf = y.to(torch.float32).contiguous()
+    return _Chamfer.apply(xf, yf, int(norm), int(point_reduction == "mean"), int(batch_reduction == "mean")), None

@@ -39,6 +39,10 @@ struct aurdf_ctx {
     std::mutex lock;
 };
 
+namespace aurdf {
+void set_concurrent_sweeps(int n);   // icp_sweep.cu
+}
+
 namespace {
 using aurdf::align_up;
 
@@ -277,6 +281,7 @@ static int sweep_host_locked(aurdf_ctx *c, const void *src_xyz, int pts_dtype, c
         // per-tile arrays are shifted to the chunk's first tile; point arrays keep their base because the
         // offsets stored in src_off / box_off / tgt_off are global
         const Blk &B = blk[k];
+        aurdf::set_concurrent_sweeps(n_chunks);   // frame blocks run as concurrent launches: residency for all of them
         rc2 = aurdf_icp_sweep(di + o_src, pts_dtype, (const int32_t *)(di + o_soff) + q.t0, di + o_tgt,
                               (const int32_t *)(di + o_toff), (const int32_t *)(di + o_tf) + q.t0,
                               box_xyz ? (const void *)(di + o_box) : nullptr, box_dtype,
@@ -287,6 +292,7 @@ static int sweep_host_locked(aurdf_ctx *c, const void *src_xyz, int pts_dtype, c
                               (double *)(d_o + B.fit), (double *)(d_o + B.rmse), (int32_t *)(d_o + B.it),
                               (int32_t *)(d_o + B.nt), (char *)c->d_ws + q.ws_off, q.ws_bytes, q.cap,
                               (int32_t *)(d_o + B.status), st);
+        aurdf::set_concurrent_sweeps(1);
         if (rc2 != AURDF_OK) return rc2;
         // optimistic: queue the status and every output behind the kernels; if the capacity guess was
         // too small the chunk is simply run again (inputs already resident)

@@ -570,6 +570,14 @@ struct IcpParams {
     int n_tiles;
     int *queue;            // small-tile kernel v2: next tile to take (zeroed by tile_scan_kernel)
     int strict_nt;         // tiles with at most this many masked targets fit their poses in strict mode
+    // grid-pruned search (icp_grid.cu): medium / large tiles
+    int grid_on;           // 0: every non-small tile runs in the brute-force general kernel
+    int grid_cs;           // CTAs per tile of the grid kernel launched for this sweep (1 or 8)
+    int grid_pcap;         // most source points one of its CTAs keeps in shared memory
+    int grid_smem_bytes;   // shared memory of a CTA set aside for the tile's sorted targets + cell table
+    float4 *gs;            // workspace: cell-sorted float32 targets (x, y, z about the tile origin, compacted index)
+    int *gends;            // workspace: end offset of every grid cell, tile b at toff[b] + 2 b
+    float *gpar;           // workspace: 8 floats per tile (grid origin, cell size, 1 / cell size, max |coordinate|, cells per axis)
 };
 
 // Tile classes.  A "small" tile keeps its whole state in < 30 KB of shared memory, so that 7 tiles
@@ -581,6 +589,36 @@ constexpr int kSmNt32 = 2 * kSmPairs - 8;   // most masked targets of a small ti
 constexpr int kSmNt64 = 384;   // most targets whose float64 copy also lives in shared memory
 __device__ __forceinline__ bool tile_is_small(int ns, int nt) { return ns <= kSmNs && nt <= kSmNt32; }
 constexpr int kS2Ns = 384;     // small-tile kernel v2: most source points (three rounds of 128 home slots)
+
+// Tile classes of one sweep: small (icp_small*.cu), grid (icp_grid.cu), general (icp_tiles_kernel).  Every kernel
+// evaluates the same predicate and leaves the tiles it does not own.
+__device__ __forceinline__ bool tile_uses_small(const IcpParams &p, int ns_tile, int nt) {
+    return p.small_on && ns_tile <= p.small_ns && nt <= p.small_nt;
+}
+__device__ __forceinline__ bool tile_uses_grid(const IcpParams &p, int ns_tile, int nt) {
+    if (!p.grid_on || tile_uses_small(p, ns_tile, nt)) return false;
+    if (p.grid_cs == 1) return true;   // one CTA per tile: everything the small-tile kernel leaves
+    // cluster variant: rank-deficient tiles (strict pose fit: one CTA sums in source order) and slices beyond
+    // the shared-memory bound stay with the general kernel
+    return nt > p.strict_nt && (ns_tile + p.grid_cs - 1) / p.grid_cs <= p.grid_pcap;
+}
+
+// Sum 16 per-lane values over the 32 lanes of a warp with 16 shuffles (a transposing
+// butterfly: every step halves the number of values a lane carries).  Afterwards v[0] holds
+// the warp total of value number (lane >> 1).
+__device__ __forceinline__ void warp_sum16(double (&v)[16], int lane) {
+#pragma unroll
+    for (int half = 8, off = 16; half >= 1; half >>= 1, off >>= 1) {
+        const bool hi = (lane & off) != 0;
+#pragma unroll
+        for (int k = 0; k < half; ++k) {
+            const double send = hi ? v[k] : v[k + half];
+            const double keep = hi ? v[k + half] : v[k];
+            v[k] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+    }
+    v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+}
 
 // x' = ((m0 x + m1 y) + m2 z) + m3, each operation rounded (open3d PointCloud::Transform)
 __device__ __forceinline__ double affine_row(const double *m, double x, double y, double z) {

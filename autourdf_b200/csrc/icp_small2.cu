@@ -436,7 +436,18 @@ icp_small2_kernel(const IcpParams p) {
                 stamp(20);   // totals loaded, covariance formed
                 {
                     if (!kabsch_rotation_newton4(sigma, R)) {   // reflection / rank-deficient / large step: Jacobi SVD, warm-started
-                        kabsch_rotation(sigma, R, s_warm, have_warm);
+                        // (copies: the out-of-line call takes addresses, and sigma / R must stay in registers
+                        // on the fast path)
+                        double sg2[3][3], R2[3][3];
+#pragma unroll
+                        for (int r = 0; r < 3; ++r)
+#pragma unroll
+                            for (int cc = 0; cc < 3; ++cc) sg2[r][cc] = sigma[r][cc];
+                        kabsch_rotation(sg2, R2, s_warm, have_warm);
+#pragma unroll
+                        for (int r = 0; r < 3; ++r)
+#pragma unroll
+                            for (int cc = 0; cc < 3; ++cc) R[r][cc] = R2[r][cc];
                         have_warm = true;
                     }
                     stamp(21);   // rotation fitted
@@ -540,6 +551,10 @@ icp_small2_kernel(const IcpParams p) {
             if (lane < 16) s_T[lane] = v;
         };
 
+        // The serial roles rotate with the tile: the warps of the CTAs resident on one SM map onto its four
+        // schedulers by warp index, so a fixed "warp 0 fits the pose" piles every resident tile's serial section on
+        // one scheduler (measured: 2.1x the instructions of the average scheduler, profiles/r02a_kernels.json).
+        const int fit_w = b & 3, conv_w = (b + 1) & 3, comp_w = (b + 3) & 3;
         // it = -1 is open3d's initial correspondence pass (no update applied); one copy of every phase
         // keeps the loop body small enough for the instruction caches.
         int iters = 0;
@@ -547,15 +562,15 @@ icp_small2_kernel(const IcpParams p) {
         for (int it = -1; it < p.max_iter; ++it) {
             const bool apply = it >= 0;
             stamp(0);   // iteration start
-            if (apply && warp == kWarps - 1) compose_pose();   // uses s_U of this iteration; its next write is after barrier A
+            if (apply && warp == comp_w) compose_pose();   // uses s_U of this iteration; its next write is after barrier A
             pass(apply);
             stamp(5);   // pass done
             reduce();
             stamp(7);   // moment sums done
             __syncthreads();   // barrier A: partial sums visible
             stamp(8);
-            if (warp == 0) {
-                // speculative: the fit for iteration it+1 runs while warp 1 decides whether to stop
+            if (warp == fit_w) {
+                // speculative: the fit for iteration it+1 runs while the next warp decides whether to stop
                 if (it + 1 < p.max_iter) {
                     if (lane < 16) {
                         double v = s_part[0][lane >> 2][lane & 3];
@@ -567,7 +582,7 @@ icp_small2_kernel(const IcpParams p) {
                     if (s_strict) fit_strict();
                     else if (lane == 0) fit_fast();
                 }
-            } else if (warp == 1) {
+            } else if (warp == conv_w) {
                 if (lane == 0) {
                     double cnt = s_part[0][0][0], d2 = s_part[0][0][4];
 #pragma unroll

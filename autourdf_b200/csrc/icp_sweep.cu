@@ -38,9 +38,10 @@ constexpr int kIcpWarps = kIcpThreads / 32;
 constexpr int kQChunk = 1024;     // target points staged per shared-memory chunk (24 KB f64 SoA + 16 KB float4)
 constexpr int kClusterCtas = 8;   // CTAs per tile in the cluster variant (large tiles)
 constexpr int kPSmemMax = 2048;   // most source points a tile may keep in shared memory
+constexpr int kGridPcapMax = 2048; // most source points a CTA of the grid kernel keeps in shared memory (44 B each)
 
 struct WsLayout {
-    size_t box, cnt, toff, qx, qy, qz, qi, pspill, status, total;
+    size_t box, cnt, toff, qx, qy, qz, qi, pspill, status, gs, gends, gpar, total;
 };
 
 static WsLayout make_layout(int64_t B, int64_t total_src, int64_t cap) {
@@ -60,6 +61,9 @@ static WsLayout make_layout(int64_t B, int64_t total_src, int64_t cap) {
     L.qz = take((size_t)cap * sizeof(double));
     L.qi = take((size_t)cap * sizeof(int));
     L.pspill = take((size_t)total_src * 3 * sizeof(double));
+    L.gs = take((size_t)cap * sizeof(float4));
+    L.gends = take((size_t)(cap + 2 * B + 2) * sizeof(int));
+    L.gpar = take((size_t)B * 8 * sizeof(float));
     L.total = o;
     return L;
 }
@@ -274,23 +278,6 @@ mask_fill_kernel(const void *__restrict__ tgt_xyz, int pts_dtype, const int *__r
 // ------------------------------------------------------------------------------------------
 // 4. fused per-tile ICP
 // ------------------------------------------------------------------------------------------
-// Sum 16 per-lane values over the 32 lanes of a warp with 16 shuffles (a transposing
-// butterfly: every step halves the number of values a lane carries).  Afterwards v[0] holds
-// the warp total of value number (lane >> 1).
-__device__ __forceinline__ void warp_sum16(double (&v)[16], int lane) {
-#pragma unroll
-    for (int half = 8, off = 16; half >= 1; half >>= 1, off >>= 1) {
-        const bool hi = (lane & off) != 0;
-#pragma unroll
-        for (int k = 0; k < half; ++k) {
-            const double send = hi ? v[k] : v[k + half];
-            const double keep = hi ? v[k + half] : v[k];
-            v[k] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-        }
-    }
-    v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
-}
-
 // One CTA per tile, resident until that tile's ICP has converged.  Per iteration:
 //   pass      every warp: P <- U P (fused), brute-force NN of its source points against the
 //             target chunk in shared memory, 16 moment sums + inlier count per warp
@@ -345,7 +332,7 @@ icp_tiles_kernel(const IcpParams p) {
     const int ns = min(ns_tile, lo + per) - lo;
     const int nt = p.cnt[b];
     const long long q0 = p.toff[b];
-    if (p.small_on && ns_tile <= p.small_ns && nt <= p.small_nt) return;   // the small-tile kernel owns this tile (whole cluster leaves)
+    if (tile_uses_small(p, ns_tile, nt) || tile_uses_grid(p, ns_tile, nt)) return;   // another kernel owns this tile (whole cluster leaves)
     const bool resident = nt <= kQChunk;
     const int nchunks = (nt + kQChunk - 1) / kQChunk;
 
@@ -655,8 +642,17 @@ icp_tiles_kernel(const IcpParams p) {
             for (int r = 0; r < 3; ++r)
 #pragma unroll
                 for (int cc = 0; cc < 3; ++cc) sigma[r][cc] = t[7 + 3 * r + cc] * inv - mb[r] * ma[cc];
-            if (!kabsch_rotation_newton(sigma, R)) {
-                kabsch_rotation(sigma, R, s_warm, have_warm);  // reflection / rank-deficient / large step
+            if (!kabsch_rotation_newton(sigma, R)) {   // reflection / rank-deficient / large step
+                double sg2[3][3], R2[3][3];   // copies: the out-of-line call takes addresses, sigma / R stay in registers
+#pragma unroll
+                for (int r = 0; r < 3; ++r)
+#pragma unroll
+                    for (int cc = 0; cc < 3; ++cc) sg2[r][cc] = sigma[r][cc];
+                kabsch_rotation(sg2, R2, s_warm, have_warm);
+#pragma unroll
+                for (int r = 0; r < 3; ++r)
+#pragma unroll
+                    for (int cc = 0; cc < 3; ++cc) R[r][cc] = R2[r][cc];
                 have_warm = true;
             }
             const double mua[3] = {ma[0] + ox, ma[1] + oy, ma[2] + oz};
@@ -839,6 +835,7 @@ extern "C" __attribute__((visibility("default"))) void aurdf_debug_set_clock_buf
 namespace aurdf {
 int launch_icp_small(const IcpParams &P, int n_tiles, int minb, cudaStream_t stream);
 int launch_icp_small2(const IcpParams &P, int n_tiles, int minb, cudaStream_t stream);
+int launch_icp_grid(const IcpParams &P, int n_tiles, cudaStream_t stream);
 }
 
 // Tuning knobs for A/B measurements, read from the environment once (immutable afterwards; C++11
@@ -847,8 +844,11 @@ int launch_icp_small2(const IcpParams &P, int n_tiles, int minb, cudaStream_t st
 //   AURDF_ICP_SMALL_MINB   resident CTAs per SM the small-tile kernel is compiled for
 //   AURDF_ICP_SMALL_SPLIT  0: every round of a tile uses the same lane split (icp_small_kernel only)
 //   AURDF_ICP_STRICT_NT    tiles with at most this many masked targets use the strict pose fit (v2)
+//   AURDF_ICP_GRID         0: no grid-pruned search (non-small tiles scan every target); 1 (default): icp_grid_kernel
+//   AURDF_ICP_GRID_CS_NS   source points per tile above which the grid kernel runs as 8-CTA clusters
+//   AURDF_ICP_GRID_SMEM_KB shared memory per CTA for a tile's sorted targets + cell table (one-CTA variant)
 struct Tuning {
-    int small, minb, split, strict_nt;
+    int small, minb, split, strict_nt, grid, grid_cs_ns, grid_smem_kb;
 };
 static const Tuning &tuning() {
     static const Tuning t = [] {
@@ -858,12 +858,29 @@ static const Tuning &tuning() {
         };
         Tuning v;
         v.small = geti("AURDF_ICP_SMALL", 2);
-        v.minb = geti("AURDF_ICP_SMALL_MINB", 6);
+        v.minb = geti("AURDF_ICP_SMALL_MINB", 0);   // 0: chosen per call, see small_tile_residency()
         v.split = geti("AURDF_ICP_SMALL_SPLIT", 1);
         v.strict_nt = geti("AURDF_ICP_STRICT_NT", 16);
+        v.grid = geti("AURDF_ICP_GRID", 1);
+        v.grid_cs_ns = geti("AURDF_ICP_GRID_CS_NS", 1024);
+        v.grid_smem_kb = geti("AURDF_ICP_GRID_SMEM_KB", 64);
         return v;
     }();
     return t;
+}
+
+// Residency the small-tile kernel is compiled for.  Measured (profiles/r02_notes.md): one launch per step runs
+// fastest with 4 CTAs per SM (122 registers, no spills; the launch is bound by its slowest tile, not by
+// occupancy); the host path, whose frame blocks run as concurrent launches on separate streams, with 6 (every
+// tile of every block resident at once).
+static thread_local int g_concurrent_sweeps = 1;
+namespace aurdf {
+void set_concurrent_sweeps(int n) { g_concurrent_sweeps = n > 0 ? n : 1; }
+}
+static int small_tile_residency() {
+    const int forced = tuning().minb;
+    if (forced >= 4 && forced <= 6) return forced;
+    return g_concurrent_sweeps > 1 ? 6 : 4;
 }
 
 extern "C" int aurdf_icp_sweep_launches(void) { return tuning().small ? 5 : 4; }
@@ -974,6 +991,18 @@ extern "C" int aurdf_icp_sweep(const void *src_xyz, int pts_dtype, const int32_t
     P.n_tiles = n_tiles;
     P.queue = status_int + 3;
     P.strict_nt = tn.strict_nt;
+    // grid-pruned search for the tiles the small-tile kernel does not take: one CTA per tile, or an 8-CTA
+    // cluster when the caller announces tiles of more than grid_cs_ns source points
+    P.grid_on = tn.grid != 0;
+    P.grid_cs = max_src_per_tile > tn.grid_cs_ns ? kClusterCtas : 1;
+    P.grid_pcap = ((max_src_per_tile > 0 ? max_src_per_tile : 256) + P.grid_cs - 1) / P.grid_cs;
+    if (P.grid_pcap > kGridPcapMax) P.grid_pcap = kGridPcapMax;
+    P.grid_pcap = (P.grid_pcap + 3) & ~3;
+    // one CTA per tile: 64 KB for the grid (n_t <= ~3200) keeps two CTAs per SM; cluster variant (few, large
+    // tiles): whatever one CTA per SM leaves after the source-point state and the static arrays
+    P.grid_smem_bytes = P.grid_cs == 1 ? tn.grid_smem_kb * 1024 : (227 - 4) * 1024 - P.grid_pcap * 44;
+    if (P.grid_smem_bytes < 0) P.grid_smem_bytes = 0;
+    P.gs = (float4 *)(ws + L.gs); P.gends = (int *)(ws + L.gends); P.gpar = (float *)(ws + L.gpar);
     EvPair ev{nullptr, nullptr};
     if (g_prof_on) {
         AURDF_CUDA_CHECK(cudaEventCreate(&ev.a));
@@ -983,10 +1012,17 @@ extern "C" int aurdf_icp_sweep(const void *src_xyz, int pts_dtype, const int32_t
     // small tiles first (one CTA each, all resident at once); the general kernel's CTAs for those
     // tiles exit immediately, and vice versa
     if (P.small_on) {
-        const int rc = tn.small == 2 ? launch_icp_small2(P, n_tiles, tn.minb, stream) : launch_icp_small(P, n_tiles, tn.minb, stream);
+        const int rc = tn.small == 2 ? launch_icp_small2(P, n_tiles, small_tile_residency(), stream) : launch_icp_small(P, n_tiles, small_tile_residency(), stream);
         if (rc != AURDF_OK) return rc;
     }
-    if (use_cluster) {
+    if (P.grid_on) {
+        const int rc = launch_icp_grid(P, n_tiles, stream);
+        if (rc != AURDF_OK) return rc;
+    }
+    // the brute-force general kernel is only needed without the grid kernel, or beside its cluster variant
+    // (rank-deficient large tiles, slices beyond the shared-memory bound)
+    if (P.grid_on && P.grid_cs == 1) {
+    } else if (use_cluster) {
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3((unsigned)n_tiles * kClusterCtas);
         cfg.blockDim = dim3(kIcpThreads);

@@ -15,7 +15,7 @@ reference's convergence rule.  Synthetic data (autourdf_b200.synth), float64 ari
   e2e       the same through the host-buffer C-ABI call (aurdf_icp_sweep_host): numpy in,
             numpy out, H2D + D2H copies inside the timed region (the call cuts the batch into
             three frame blocks on separate streams so copies and kernels overlap)
-  roofline  the fused per-tile ICP kernel (icp_small_kernel: every wx200_5 tile is in its class):
+  roofline  the fused per-tile ICP kernel (icp_small2_kernel: every wx200_5 tile is in its class):
             algorithmic bytes / its measured duration vs the measured HBM peak
             (MEASURED_PEAKS.json), plus the instruction-issue fraction that actually binds it
   cpu_baseline / --impl reference: the CPU restatement (oracle/, k-d tree NN, OpenMP over
@@ -442,15 +442,15 @@ def main():
         achieved = b_alg / (k_ms * 1e-3) / 1e9
         pairs = float((ns * ntgt * (iters + 1)).sum())             # distance evaluations per launch
         sm_hz = (clocks.get("sm_mhz") or 1965.0) * 1e6
-        # The roof that binds is instruction issue, not HBM: the float32 pre-filter of icp_small_kernel
+        # The roof that binds is instruction issue, not HBM: the float32 pre-filter of icp_small2_kernel
         # issues 17 instructions per PAIR of targets (2 LDS.128, 6 packed f32x2, 2 LOP3, 4 VIMNMX,
         # 1 VIMNMX3, ~2 loop; SASS count), i.e. 8.5 per (source, target) evaluation; exact float64 work
         # is O(1) per point; peak = 148 SMs x 4 schedulers x 32 lanes per clock.
         instr_per_pair = 8.5
         issue_peak = 148 * 128 * sm_hz
         issue_rate = instr_per_pair * pairs / (k_ms * 1e-3)
-        small = bool(ns.size and ns.max() <= 320 and ntgt.max() <= 760)
-        kname = "icp_small_kernel" if small else "icp_tiles_kernel"
+        small = bool(ns.size and ns.max() <= 384 and ntgt.max() <= 760)
+        kname = "icp_small2_kernel" if small else "icp_grid_kernel"
         traffic, traffic_src = load_traffic(kname)
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                     "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,

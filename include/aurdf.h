@@ -160,6 +160,28 @@ AURDF_API int aurdf_nn_f32_bwd(const float *p1_xyz, const int32_t *p1_off, const
                                float *grad_p2, aurdf_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------
+ * Fused chamfer distance: pytorch3d 0.7.7 loss.chamfer_distance(x, y, norm=1|2) exactly as the reference calls
+ * it (PointCloud/mlp_reg.py:96 inside the 300-epoch train() loop, ~600 calls per frame at P ~ 5000;
+ * Sim/evaluation.py:81) -- both nearest-neighbour directions, the point / batch reductions and the scalar loss
+ * in ONE kernel launch; the backward (knn_points' backward for both directions) in one more.
+ *   x (N, P1, 3), y (N, P2, 3) contiguous float32;  point_mean / batch_mean: 1 = "mean", 0 = "sum";
+ *   idx_x (N*P1) / idx_y (N*P2): nearest neighbour of every point in the other cloud (kept for the backward);
+ *   loss: one float (device);  grad_loss: one float (device), the upstream gradient;
+ *   grad_x / grad_y: zero-initialised by the caller, either may be NULL.
+ * workspace: aurdf_chamfer_workspace_bytes(N, P1, P2) bytes, 256-byte aligned, initialised ONCE with
+ * aurdf_chamfer_workspace_init (arrival counters; the kernel resets them itself) and then reused by every call
+ * of the same shape; one workspace must not be used by two calls that may run concurrently.
+ * ------------------------------------------------------------------------------------- */
+AURDF_API size_t aurdf_chamfer_workspace_bytes(int32_t n_batch, int32_t p1, int32_t p2);
+AURDF_API int aurdf_chamfer_workspace_init(void *workspace, size_t workspace_bytes, aurdf_stream_t stream);
+AURDF_API int aurdf_chamfer_fwd(const float *x, const float *y, int32_t n_batch, int32_t p1, int32_t p2, int norm,
+                                int point_mean, int batch_mean, int32_t *idx_x, int32_t *idx_y, float *loss,
+                                void *workspace, size_t workspace_bytes, aurdf_stream_t stream);
+AURDF_API int aurdf_chamfer_bwd(const float *x, const float *y, const int32_t *idx_x, const int32_t *idx_y,
+                                const float *grad_loss, int32_t n_batch, int32_t p1, int32_t p2, int norm,
+                                int point_mean, int batch_mean, float *grad_x, float *grad_y, aurdf_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
  * SE(3) apply: calculate_pc(), PointCloud/mlp_reg.py:155-170:  out = X @ R_k^T + t_k for
  * every point of group k (dtype F32 or F64 for points, poses and output alike).
  * aurdf_se3_apply_bwd is its adjoint for autograd: grad_X = g R_k, grad_T[k][:3,:3] =

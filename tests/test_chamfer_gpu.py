@@ -81,3 +81,42 @@ def test_chamfer_reference_call_shape():
     assert np.abs(pred.grad.cpu().numpy() - ogx).max() <= 1e-6
     with pytest.raises(ValueError):
         chamfer_distance(pred, y.unsqueeze(0), norm=3)
+
+
+@pytest.mark.parametrize("N,P1,P2", [(1, 1, 1), (1, 37, 5), (3, 700, 1500), (1, 5000, 5000), (2, 513, 64), (1, 20000, 3000)])
+def test_fused_chamfer_matches_packed_knn_and_is_repeatable(N, P1, P2):
+    """the one-launch forward: nearest-neighbour indices (kept for the backward) identical to the packed
+    aurdf_nn_f32 path (itself bit-exact against the oracle), loss within float32 summation error of the oracle,
+    and -- the arrival counters reset themselves -- bit-identical on repeated calls"""
+    from autourdf_b200 import chamfer as ch
+    from oracle import chamfer_oracle as O
+    rng = np.random.default_rng(N * 1000 + P1 + P2)
+    x = rng.normal(0, 0.2, (N, P1, 3)).astype(np.float32)
+    y = rng.normal(0, 0.2, (N, P2, 3)).astype(np.float32)
+    y[0, 0] = x[0, 0]                                                # one exact coincidence
+    xt, yt = torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda()
+    losses = []
+    for norm in (1, 2):
+        ol = O.chamfer_distance(x, y, norm)[0]
+        for rep in range(3):
+            xr = xt.clone().requires_grad_(True)
+            loss, _ = ch.chamfer_distance(xr, yt, norm=norm)
+            loss.backward()
+            losses.append((norm, loss.item(), xr.grad.abs().sum().item()))
+            assert abs(loss.item() - ol) <= 4e-6 * abs(ol) + 1e-12
+        assert losses[-1][1] == losses[-2][1] == losses[-3][1], "loss differs between identical calls"
+        xo = torch.arange(0, (N + 1) * P1, P1, dtype=torch.int32, device="cuda")
+        yo = torch.arange(0, (N + 1) * P2, P2, dtype=torch.int32, device="cuda")
+        ix, dx = ch.knn1(xt.reshape(-1, 3), xo, yt.reshape(-1, 3), yo, norm)
+        iy, dy = ch.knn1(yt.reshape(-1, 3), yo, xt.reshape(-1, 3), xo, norm)
+        # indices saved by the fused forward (through the autograd node of a fresh call)
+        xr = xt.clone().requires_grad_(True)
+        loss, _ = ch.chamfer_distance(xr, yt, norm=norm)
+        idx = loss.grad_fn.saved_tensors[2]
+        assert torch.equal(idx[:N * P1], ix) and torch.equal(idx[N * P1:], iy)
+        for red in (("sum", "mean"), ("mean", "sum"), ("sum", "sum")):
+            l2, _ = ch.chamfer_distance(xt, yt, norm=norm, batch_reduction=red[0], point_reduction=red[1])
+            cx = dx.reshape(N, P1).double().sum(1) / (P1 if red[1] == "mean" else 1)
+            cy = dy.reshape(N, P2).double().sum(1) / (P2 if red[1] == "mean" else 1)
+            want = (cx.sum() + cy.sum()) / (N if red[0] == "mean" else 1)
+            assert abs(l2.item() - want.item()) <= 4e-6 * abs(want.item()) + 1e-12

@@ -307,3 +307,74 @@ def test_tile_class_boundaries(oracle):
         assert np.array_equal(corr[s_off[n]:s_off[n + 1]], o["corr"]), f"correspondences differ for {cases[i]}"
         assert np.abs(T[n] - o["T"]).max() <= 1e-5
         assert abs(fit[n] - o["fitness"]) <= 1e-12 and abs(rmse[n] - o["rmse"]) <= 1e-9
+
+
+def test_grid_search_adversarial(oracle):
+    """Shapes that stress the grid-pruned exact search of icp_grid_kernel (medium / large tiles): sources far
+    outside the targets' bounding box (every block widening path), flat and rod-like target sets (degenerate
+    grid axes), duplicated targets (exact ties -> lowest index), a lattice (many near-ties), a rank-deficient
+    large tile (strict pose fit in the one-CTA variant), a tight correspondence threshold, and the same shapes
+    both as one-CTA tiles and -- with a large tile in the batch -- as 8-CTA cluster tiles."""
+    import torch
+    from scipy.spatial.transform import Rotation
+    from autourdf_b200 import cluster_icp as ci
+    rng = np.random.default_rng(17)
+    f32 = lambda a: np.ascontiguousarray(a, dtype=np.float32).astype(np.float64)
+
+    def moved(tgt, ns, rot=0.03, shift=2e-3, noise=5e-4):
+        R = Rotation.from_rotvec(rng.normal(scale=rot, size=3)).as_matrix()
+        pick = tgt[rng.integers(0, tgt.shape[0], size=ns)] + rng.normal(scale=noise, size=(ns, 3))
+        return f32((pick - rng.normal(scale=shift, size=3)) @ R)
+
+    cases = {}
+    surf = rng.uniform(-0.1, 0.1, size=(3000, 3)); surf[:, 2] = 0.02 * np.sin(20 * surf[:, 0])     # a curved sheet
+    cases["sheet"] = (moved(f32(surf), 900), f32(surf), 1.0)
+    vol = f32(rng.uniform(-0.05, 0.05, size=(2500, 3)))
+    cases["outside"] = (f32(moved(vol, 700) + [0.03, -0.02, 0.025]), vol, 1.0)                     # starts half a box away
+    far = (f32(moved(vol, 700) + [0.4, -0.3, 0.25]), vol)   # 0.5 m away: every source sees the same corner (rank-deficient
+                                                            # fit), so only the initial correspondence pass is compared
+    flat = rng.uniform(-0.1, 0.1, size=(1500, 3)); flat[:, 1] = rng.normal(scale=1e-4, size=1500)   # one grid cell thick
+    cases["flat"] = (moved(f32(flat), 600), f32(flat), 1.0)
+    line = rng.normal(scale=1.5e-3, size=(900, 3)); line[:, 0] = np.linspace(-0.1, 0.1, 900)        # a thin rod
+    cases["rod"] = (moved(f32(line), 500, rot=0.01), f32(line), 1.0)
+    dup = f32(rng.uniform(-0.05, 0.05, size=(600, 3)))
+    dup = np.concatenate([dup, dup[::3], dup[::7]])                                                # exact duplicates
+    cases["duplicates"] = (moved(dup, 800), dup, 1.0)
+    g = np.linspace(-0.05, 0.05, 12)
+    lat = f32(np.stack(np.meshgrid(g, g, g, indexing="ij"), -1).reshape(-1, 3))
+    cases["lattice"] = (moved(lat, 1000, rot=0.01, shift=1e-3, noise=0.0), lat, 1.0)
+    cases["tight_threshold"] = (moved(vol, 800), vol, 0.004)
+    cases["few_targets"] = (f32(rng.uniform(-0.05, 0.05, size=(600, 3))), f32(rng.uniform(-0.05, 0.05, size=(3, 3))), 1.0)
+    big = f32(rng.uniform(-0.1, 0.1, size=(12000, 3)))
+    dev = torch.device("cuda")
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+
+    def run(names, th, extra=None, max_iter=60):
+        srcs = [cases[n][0] for n in names] + ([extra[0]] if extra else [])
+        tgts = [cases[n][1] for n in names] + ([extra[1]] if extra else [])
+        s_off = np.concatenate([[0], np.cumsum([s.shape[0] for s in srcs])]).astype(np.int32)
+        t_off = np.concatenate([[0], np.cumsum([q.shape[0] for q in tgts])]).astype(np.int32)
+        r = ci.icp_sweep(t(np.concatenate(srcs)), t(s_off), t(np.concatenate(tgts)), t(t_off),
+                         t(np.arange(len(srcs), dtype=np.int32)), None, None, t(np.stack([np.eye(4)] * len(srcs))),
+                         max_src_per_tile=int(np.diff(s_off).max()), max_corr=th, max_iter=max_iter)
+        torch.cuda.synchronize()
+        return r, s_off, srcs, tgts
+
+    cases["far"] = (far[0], far[1], -1.0)
+    r, s_off, srcs, tgts = run(["far", "sheet"], 1.0, max_iter=0)
+    o = oracle.icp_p2p(far[0], far[1], 1.0, np.eye(4), max_iter=0, use_kdtree=True)
+    assert np.array_equal(r.corr.cpu().numpy()[:s_off[1]], o["corr"]), "far: initial correspondences differ"
+    r, s_off, srcs, tgts = run(["far"], 1.0, (moved(big, 9000), big), max_iter=0)
+    assert np.array_equal(r.corr.cpu().numpy()[:s_off[1]], o["corr"]), "far (cluster variant): initial correspondences differ"
+    for th in (1.0, 0.004):
+        names = [n for n, c in cases.items() if c[2] == th]
+        for extra in (None, (moved(big, 9000), big)):          # without / with a tile that switches on the cluster variant
+            r, s_off, srcs, tgts = run(names, th, extra)
+            corr, iters, T = r.corr.cpu().numpy(), r.iters.cpu().numpy(), r.T.cpu().numpy()
+            for n in range(len(srcs)):
+                o = oracle.icp_p2p(srcs[n], tgts[n], th, np.eye(4), max_iter=60, use_kdtree=True)
+                name = names[n] if n < len(names) else "big"
+                assert iters[n] == o["iters"], f"{name}: iterations {iters[n]} vs {o['iters']}"
+                bad = np.nonzero(corr[s_off[n]:s_off[n + 1]] != o["corr"])[0]
+                assert bad.size == 0, f"{name}: {bad.size} correspondences differ (cluster variant: {extra is not None})"
+                assert np.abs(T[n] - o["T"]).max() <= 1e-5, name
