@@ -569,6 +569,7 @@ struct IcpParams {
     int small_ns, small_nt;   // class bounds of the small-tile kernel in use (source points, masked targets)
     int n_tiles;
     int *queue;            // small-tile kernel v2: next tile to take (zeroed by tile_scan_kernel)
+    int *queue2;           // grid kernel, one-CTA variant: its own tile queue (zeroed by tile_scan_kernel)
     int strict_nt;         // tiles with at most this many masked targets fit their poses in strict mode
     // grid-pruned search (icp_grid.cu): medium / large tiles
     int grid_on;           // 0: every non-small tile runs in the brute-force general kernel

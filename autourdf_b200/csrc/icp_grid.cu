@@ -6,25 +6,34 @@
 // correspondence query from a k-d tree; a brute-force scan is O(n_s n_t) per iteration and is what
 // bounded the large tiles of the C5 sweep.  Here:
 //
-//   grid_build_kernel   one CTA per tile: a uniform grid over the bounding box of the tile's masked targets
-//                       (about one target per cell by volume, at most 64 cells per axis), counting sort of
-//                       the targets by cell into float32 records (x, y, z about the tile origin, compacted
-//                       index) + the end offset of every cell.
-//   icp_grid_kernel<CS> one CTA (CS = 1) or a thread-block cluster of CS CTAs per tile, one thread per
-//                       source point.  A query scans a block of cells: the 3x3x3 neighbourhood of its
-//                       own cell, widened to the cube that holds the ball through the previous winner.
-//                       The float32 scan keeps best and second best; targets in cells outside the block
-//                       are at least as far as the nearest face of the block.  If
-//                       min(second best, face distance)^2 - best > 2 tau (tau over-covers every float32
-//                       rounding) the float32 winner is provably the float64 argmin and only its exact
+//   build_grid          (device function; its own launch, grid_build_kernel, for the cluster variant) a uniform grid
+//                       over the bounding box of the tile's masked targets -- about one target per cell by
+//                       volume, at most 64 cells per axis -- and a counting sort of the targets by cell into
+//                       float32 records (x, y, z about the tile origin, compacted index) + the end offset of
+//                       every cell.
+//   icp_grid_kernel<CS> CS = 1: persistent 512-thread CTAs take the tiles the small-tile kernel leaves from a
+//                       queue; CS = 8: a thread-block cluster per tile, every CTA a slice of the source points.
+//                       The sorted targets and the cell table are staged in shared memory when they fit (explicit
+//                       ld.shared), the source points of a CTA are kept in Morton order of their cells so that a
+//                       warp's queries walk overlapping blocks, one thread per source point.  A query scans a
+//                       block of cells: the 3x3x3 neighbourhood of its own cell, widened to the cube that holds
+//                       the ball through the previous winner.  The float32 scan keeps best and second best;
+//                       targets in cells outside the block are at least as far as the nearest face of the
+//                       block.  If min(second best, face distance^2) - best > 2 tau (tau over-covers every
+//                       float32 rounding) the float32 winner is provably the float64 argmin and only its exact
 //                       distance is evaluated, in the reference's operation order; otherwise the block is
-//                       rescanned in float64 (lowest index on ties) and grown until the face distance
-//                       clears the winner.  The same quantities certify a nearest-neighbour cache
-//                       (anchor, winner, rho) exactly as in icp_small2.cu, so most points skip the scan
-//                       once the pose settles.
+//                       rescanned in float64 (lowest index on ties) and grown until the face distance clears the
+//                       winner.  The same quantities certify a nearest-neighbour cache (anchor, winner, rho)
+//                       exactly as in icp_small2.cu, so about half the points skip the scan once the pose settles.
+//
+// Measured alternatives (profiles/r02_notes.md): eight lanes per query, miss lists + one warp per large block,
+// work items of eight candidates dealt to all threads, and one in-step scan of a warp's bounding block were all
+// slower than the per-lane walk over Morton-ordered queries.
 //
 // Pose fit, convergence rule, pose composition and outputs are those of icp_tiles_kernel.
 #include <math.h>
+
+#include <type_traits>
 
 #include <cooperative_groups.h>
 
@@ -35,15 +44,41 @@ namespace cg = cooperative_groups;
 namespace aurdf {
 
 namespace {
-constexpr int kGT = 256;
+constexpr int kGT = 512;
 constexpr int kGW = kGT / 32;
+constexpr int kGridSortMax = 2048;   // most source points of a CTA (sorted by cell at tile start)
 
 struct GridView {
     const float4 *gs;   // cell-sorted targets of this tile
     const int *ends;    // end offset of every cell (start = end of the previous cell)
+    uint32_t gs_s, ends_s;   // the same as shared-space addresses when the grid has been staged in shared memory
     float g0x, g0y, g0z, h, inv_h;
     int Gx, Gy, Gz;
 };
+
+// Grid loads.  SH = true: explicit ld.shared (the staged copy).  A generic pointer that may point to either
+// space compiles to generic loads, which the hardware serves through the global-memory path's scoreboard even
+// when the address is in shared memory: measured ~10x the latency of LDS in the dependent walk of a scan.
+template <bool SH>
+__device__ __forceinline__ int ld_end(const GridView &gv, int c) {
+    if constexpr (SH) {
+        int v;
+        asm("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(gv.ends_s + 4u * (uint32_t)c));
+        return v;
+    } else {
+        return gv.ends[c];
+    }
+}
+template <bool SH>
+__device__ __forceinline__ float4 ld_tgt(const GridView &gv, int k) {
+    if constexpr (SH) {
+        float4 v;
+        asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(gv.gs_s + 16u * (uint32_t)k));
+        return v;
+    } else {
+        return gv.gs[k];
+    }
+}
 
 __device__ __forceinline__ int cell_of(float v, float g0, float inv_h, int G) {
     const int c = __float2int_rd((v - g0) * inv_h);
@@ -54,7 +89,10 @@ struct Block {
     int lx, hx, ly, hy, lz, hz;
 };
 
-// float32 scan of a block of cells: best (m1, sorted position k1) and second best (m2) squared distance
+// float32 scan of a block of cells: best (m1, sorted position k1) and second best (m2) squared distance.
+// The source points of a CTA are sorted by cell (see the kernel), so the lanes of a warp walk (nearly) the same rows:
+// the row loop is uniform and the loads of a warp fall on the same few lines.
+template <bool SH>
 __device__ __forceinline__ void scan_block_f32(const GridView &gv, const Block &bk, float fx, float fy, float fz, float &m1,
                                                float &m2, int &k1) {
     m1 = INFINITY; m2 = INFINITY; k1 = -1;
@@ -62,10 +100,10 @@ __device__ __forceinline__ void scan_block_f32(const GridView &gv, const Block &
         for (int cy = bk.ly; cy <= bk.hy; ++cy) {
             const int row = (cz * gv.Gy + cy) * gv.Gx;
             const int a = row + bk.lx;
-            int k = a > 0 ? gv.ends[a - 1] : 0;
-            const int e = gv.ends[row + bk.hx];
+            int k = a > 0 ? ld_end<SH>(gv, a - 1) : 0;
+            const int e = ld_end<SH>(gv, row + bk.hx);
             for (; k + 1 < e; k += 2) {
-                const float4 q0 = gv.gs[k], q1 = gv.gs[k + 1];
+                const float4 q0 = ld_tgt<SH>(gv, k), q1 = ld_tgt<SH>(gv, k + 1);
                 const float dx0 = fx - q0.x, dy0 = fy - q0.y, dz0 = fz - q0.z;
                 const float dx1 = fx - q1.x, dy1 = fy - q1.y, dz1 = fz - q1.z;
                 const float d0 = fmaf(dz0, dz0, fmaf(dy0, dy0, dx0 * dx0));
@@ -78,7 +116,7 @@ __device__ __forceinline__ void scan_block_f32(const GridView &gv, const Block &
                 m1 = fminf(m1, d1);
             }
             if (k < e) {
-                const float4 q0 = gv.gs[k];
+                const float4 q0 = ld_tgt<SH>(gv, k);
                 const float dx0 = fx - q0.x, dy0 = fy - q0.y, dz0 = fz - q0.z;
                 const float d0 = fmaf(dz0, dz0, fmaf(dy0, dy0, dx0 * dx0));
                 m2 = fminf(m2, fmaxf(m1, d0));
@@ -302,14 +340,15 @@ grid_build_kernel(const IcpParams p) {
 // per-tile ICP, grid search
 // ------------------------------------------------------------------------------------------
 template <int CS>
-__global__ void __launch_bounds__(kGT, 2)
-icp_grid_kernel(const IcpParams p) {
+__device__ __forceinline__ void grid_tile(const IcpParams &p, const int b) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float4 *sanc = reinterpret_cast<float4 *>(smem_raw);            // cache: anchor (float32 frame), rho
     double *spx_s = reinterpret_cast<double *>(sanc + p.grid_pcap);   // current source points of this CTA's slice
     double *spy_s = spx_s + p.grid_pcap;
     double *spz_s = spy_s + p.grid_pcap;
     int *scj_s = reinterpret_cast<int *>(spz_s + p.grid_pcap);      // nearest target (compacted index) or -1
+    int *sord = scj_s + p.grid_pcap;                                // slot -> index of the point within the slice (cell order)
+    unsigned *skey = reinterpret_cast<unsigned *>(sord + p.grid_pcap);   // sort keys, kGridSortMax of them (setup only)
 
     __shared__ double s_part[kGW][16];
     __shared__ int s_cnt[kGW];
@@ -325,7 +364,6 @@ icp_grid_kernel(const IcpParams p) {
     if (p.status_int[0]) return;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int b = blockIdx.x / CS;
     int rank = 0;
     if constexpr (CS > 1) rank = (int)cg::this_cluster().block_rank();
     const int ns_tile = p.src_off[b + 1] - p.src_off[b];
@@ -357,6 +395,8 @@ icp_grid_kernel(const IcpParams p) {
     gv.gs = p.gs + q0;
     gv.ends = p.gends + q0 + 2 * (long long)b;
     gv.g0x = gv.g0y = gv.g0z = 0.f; gv.h = gv.inv_h = 1.f; gv.Gx = gv.Gy = gv.Gz = 1;
+    gv.gs_s = gv.ends_s = 0;
+    bool grid_sh = false;   // the grid has been staged in shared memory
     float aq = 0.f;
     if (nt > 0) {
         const float *gp = p.gpar + 8 * (size_t)b;
@@ -370,12 +410,15 @@ icp_grid_kernel(const IcpParams p) {
         const int ncells = gv.Gx * gv.Gy * gv.Gz;
         const size_t need = (size_t)nt * sizeof(float4) + (size_t)ncells * sizeof(int);
         if (need <= (size_t)p.grid_smem_bytes) {
-            float4 *sg = reinterpret_cast<float4 *>(scj_s + p.grid_pcap);   // grid_pcap is even: 16-byte aligned
+            float4 *sg = reinterpret_cast<float4 *>(skey + kGridSortMax);   // grid_pcap is a multiple of 4: 16-byte aligned
             int *se = reinterpret_cast<int *>(sg + nt);
             for (int k = tid; k < nt; k += kGT) sg[k] = gv.gs[k];
             for (int c = tid; c < ncells; c += kGT) se[c] = gv.ends[c];
             gv.gs = sg;
             gv.ends = se;
+            gv.gs_s = smem_u32(sg);
+            gv.ends_s = smem_u32(se);
+            grid_sh = true;
         }
     }
 
@@ -385,23 +428,67 @@ icp_grid_kernel(const IcpParams p) {
         s_U[tid] = (tid % 5 == 0) ? 1.0 : 0.0;
     }
     __syncthreads();
+    const double ox = nt > 0 ? __ldg(qx) : 0.0, oy = nt > 0 ? __ldg(qy) : 0.0, oz = nt > 0 ? __ldg(qz) : 0.0;
     {
         const bool aff0 = s_T[12] == 0.0 && s_T[13] == 0.0 && s_T[14] == 0.0 && s_T[15] == 1.0;
-        for (int i = tid; i < ns; i += kGT) {
+        auto posed = [&](int i, double &x, double &y, double &z) __attribute__((always_inline)) {   // P = T0 * S
             const size_t e = 3 * (size_t)(s0 + i);
-            double x = ld_coord(p.src, p.pts_dtype, e), y = ld_coord(p.src, p.pts_dtype, e + 1),
-                   z = ld_coord(p.src, p.pts_dtype, e + 2);
+            x = ld_coord(p.src, p.pts_dtype, e); y = ld_coord(p.src, p.pts_dtype, e + 1); z = ld_coord(p.src, p.pts_dtype, e + 2);
             transform_point(s_T, aff0, x, y, z);
-            px[i] = x; py[i] = y; pz[i] = z;
-            cj[i] = -1;
-            if (in_smem) sanc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        };
+        // The points of the slice are kept in Morton order of the grid cell they start in (bitonic sort of
+        // (code, index) keys, once per tile): the 32 queries of a warp then sit in a compact box of cells, walk
+        // overlapping blocks and load the same lines.  (Scanning the bounding block of a warp's queries once, in
+        // step, was measured slower: at ~1 point per cell it holds 4x the candidates of one query's block.)
+        // Strict tiles keep the source order (their sums run in ascending source index).
+        const bool sorted = in_smem && nt > 0 && !strict_tile && ns > 32;
+        if (sorted) {
+            int n2 = 64;
+            while (n2 < ns) n2 <<= 1;
+            for (int i = tid; i < n2; i += kGT) {
+                unsigned key = 0xffffffffu;
+                if (i < ns) {
+                    double x, y, z;
+                    posed(i, x, y, z);
+                    // Morton code of the cell (<= 6 bits per axis): consecutive points fill compact boxes of cells
+                    auto spread = [](unsigned v) { v &= 0x3fu; v = (v | (v << 8)) & 0x300fu; v = (v | (v << 4)) & 0x30c3u; return (v | (v << 2)) & 0x9249u; };
+                    const unsigned c = spread((unsigned)cell_of((float)(x - ox), gv.g0x, gv.inv_h, gv.Gx)) |
+                                       (spread((unsigned)cell_of((float)(y - oy), gv.g0y, gv.inv_h, gv.Gy)) << 1) |
+                                       (spread((unsigned)cell_of((float)(z - oz), gv.g0z, gv.inv_h, gv.Gz)) << 2);
+                    key = (c << 11) | (unsigned)i;   // code < 2^18, index < 2^11
+                }
+                skey[i] = key;
+            }
+            __syncthreads();
+            for (int k = 2; k <= n2; k <<= 1) {
+                for (int j = k >> 1; j > 0; j >>= 1) {
+                    for (int t = tid; t < n2; t += kGT) {
+                        const int o = t ^ j;
+                        if (o > t) {
+                            const unsigned a = skey[t], c = skey[o];
+                            if ((a > c) == ((t & k) == 0)) { skey[t] = c; skey[o] = a; }
+                        }
+                    }
+                    __syncthreads();
+                }
+            }
+        }
+        for (int t = tid; t < ns; t += kGT) {
+            const int i = sorted ? (int)(skey[t] & 0x7ffu) : t;
+            double x, y, z;
+            posed(i, x, y, z);
+            px[t] = x; py[t] = y; pz[t] = z;
+            cj[t] = -1;
+            if (in_smem) {
+                sanc[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+                sord[t] = i;
+            }
         }
     }
     __syncthreads();
-    const double ox = nt > 0 ? __ldg(qx) : 0.0, oy = nt > 0 ? __ldg(qy) : 0.0, oz = nt > 0 ? __ldg(qz) : 0.0;
     const int rounds = (ns + kGT - 1) / kGT;
 
-    auto exact_d2 = [&](double x, double y, double z, int j) {
+    auto exact_d2 = [&](double x, double y, double z, int j) __attribute__((always_inline)) {
         const double dx = __dsub_rn(x, __ldg(qx + j)), dy = __dsub_rn(y, __ldg(qy + j)), dz = __dsub_rn(z, __ldg(qz + j));
         return __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
     };
@@ -411,11 +498,14 @@ icp_grid_kernel(const IcpParams p) {
     // independent chains per warp hide more of that latency than four.)
     // debug hook (scripts/grid_stats.py): [0] queries, [1] cache hits, [2] block scans, [3] candidates evaluated,
     // [4] exact fallbacks, [5] scans of the whole grid
+    // dbg[15] selects what is recorded: 1 = counters (their atomics distort every timing), 2 = phase timers
     unsigned long long *dbg = reinterpret_cast<unsigned long long *>(p.dbg_clock);
-    auto count = [&](int k, unsigned long long v) {
-        if (dbg) atomicAdd(dbg + k, v);
+    unsigned long long *dbgc = dbg && dbg[15] == 1 ? dbg : nullptr;
+    if (dbg && dbg[15] != 2) dbg = nullptr;   // from here on dbg = timers only
+    auto count = [&](int k, unsigned long long v) __attribute__((always_inline)) {
+        if (dbgc) atomicAdd(dbgc + k, v);
     };
-    auto block_candidates = [&](const Block &bk) {
+    auto block_candidates = [&](const Block &bk) __attribute__((always_inline)) {
         unsigned long long c = 0;
         for (int cz = bk.lz; cz <= bk.hz; ++cz)
             for (int cy = bk.ly; cy <= bk.hy; ++cy) {
@@ -424,7 +514,8 @@ icp_grid_kernel(const IcpParams p) {
             }
         return c;
     };
-    auto pass = [&](bool apply) {
+    auto pass_simple = [&](bool apply, auto sh_tag) __attribute__((always_inline)) {
+        constexpr bool SH = decltype(sh_tag)::value;
         double acc[16];
 #pragma unroll
         for (int k = 0; k < 16; ++k) acc[k] = 0.0;
@@ -442,17 +533,18 @@ icp_grid_kernel(const IcpParams p) {
                     px[i] = x; py[i] = y; pz[i] = z;
                 }
             }
+            // ---- cache test (per lane)
+            const float fx = (float)(x - ox), fy = (float)(y - oy), fz = (float)(z - oz);
+            const float amag = fmaxf(aq, fmaxf(fabsf(fx), fmaxf(fabsf(fy), fabsf(fz))));
+            const float dl = 4.f * u * amag;
+            const float eps = 2e-5f * gv.h + 8.f * u * amag;
+            bool scan = false;
+            float R = -1.f;
             if (active && nt > 0) {
-                const float fx = (float)(x - ox), fy = (float)(y - oy), fz = (float)(z - oz);
-                const float amag = fmaxf(aq, fmaxf(fabsf(fx), fmaxf(fabsf(fy), fabsf(fz))));
-                const float dl = 4.f * u * amag;
-                const float eps = 2e-5f * gv.h + 8.f * u * amag;
+                scan = true;
                 const int j1c = cj[i];
-                bool scan = true;
-                float R = -1.f;
                 if (j1c >= 0) {
-                    // cache test (icp_small2.cu): the previous winner is still the float64 argmin if
-                    // d(p, winner) + |p - anchor| < rho
+                    // the previous winner is still the float64 argmin if d(p, winner) + |p - anchor| < rho (icp_small2.cu)
                     const float4 an = in_smem ? sanc[i] : make_float4(0.f, 0.f, 0.f, 0.f);
                     const double D1 = exact_d2(x, y, z, j1c);
                     const float ex = fx - an.x, ey = fy - an.y, ez = fz - an.z;
@@ -468,22 +560,26 @@ icp_grid_kernel(const IcpParams p) {
                     R = s1 * 1.01f + 64.f * dl + eps;   // the ball through the previous winner holds the new one
                 }
                 count(0, 1);
-                if (scan) {
-                    Block bk;
-                    {
-                        const int cx = cell_of(fx, gv.g0x, gv.inv_h, gv.Gx), cy = cell_of(fy, gv.g0y, gv.inv_h, gv.Gy),
-                                  cz = cell_of(fz, gv.g0z, gv.inv_h, gv.Gz);
-                        bk.lx = max(cx - 1, 0); bk.hx = min(cx + 1, gv.Gx - 1);
-                        bk.ly = max(cy - 1, 0); bk.hy = min(cy + 1, gv.Gy - 1);
-                        bk.lz = max(cz - 1, 0); bk.hz = min(cz + 1, gv.Gz - 1);
-                    }
-                    if (R >= 0.f) widen_to_radius(gv, bk, fx, fy, fz, R);
-                    float m1, m2;
-                    int k1;
+            }
+            // ---- the block of cells a scanning lane needs
+            Block bk;
+            bk.lx = bk.ly = bk.lz = 1 << 20; bk.hx = bk.hy = bk.hz = -1;
+            if (scan) {
+                const int cx = cell_of(fx, gv.g0x, gv.inv_h, gv.Gx), cy = cell_of(fy, gv.g0y, gv.inv_h, gv.Gy),
+                          cz = cell_of(fz, gv.g0z, gv.inv_h, gv.Gz);
+                bk.lx = max(cx - 1, 0); bk.hx = min(cx + 1, gv.Gx - 1);
+                bk.ly = max(cy - 1, 0); bk.hy = min(cy + 1, gv.Gy - 1);
+                bk.lz = max(cz - 1, 0); bk.hz = min(cz + 1, gv.Gz - 1);
+                if (R >= 0.f) widen_to_radius(gv, bk, fx, fy, fz, R);
+            }
+            float m1 = INFINITY, m2 = INFINITY;
+            int k1 = -1;
+            if (scan) {
+                {   // walk the block, widen it until it holds the ball through the best target found
                     int ring = 1;
                     for (;;) {
-                        scan_block_f32(gv, bk, fx, fy, fz, m1, m2, k1);
-                        if (dbg) {
+                        scan_block_f32<SH>(gv, bk, fx, fy, fz, m1, m2, k1);
+                        if (dbgc) {
                             count(2, 1);
                             count(3, block_candidates(bk));
                             if (block_is_grid(gv, bk)) count(5, 1);
@@ -497,28 +593,28 @@ icp_grid_kernel(const IcpParams p) {
                             grow_block(gv, bk, ring);
                         }
                     }
-                    bool exact = true;
-                    if (k1 >= 0) {
-                        const float fb = face_distance(gv, bk, fx, fy, fz, eps);
-                        const float m2e = fminf(m2, fb * fb);
-                        const float tau = 16.f * (dl * sqrtf(m2e) * 1.001f + dl * dl + u * m2e);
-                        if ((nt == 1 && m2e == INFINITY) || (m2e - m1 > 2.f * tau && m2e < INFINITY)) {
-                            exact = false;
-                            bj = __float_as_int(gv.gs[k1].w);
-                            bd = exact_d2(x, y, z, bj);
-                            float rho = 0.f;
-                            if (m2e == INFINITY) rho = 1e30f;
-                            else if (m2e > 128.f * dl * dl && m2e - tau > 0.f) rho = sqrtf(m2e - tau) * 0.9999f;
-                            if (in_smem) sanc[i] = make_float4(fx, fy, fz, rho);
-                        }
-                    }
-                    if (exact) {
-                        count(4, 1);
-                        scan_block_exact(gv, bk, qx, qy, qz, x, y, z, fx, fy, fz, eps, bd, bj);
-                        if (in_smem) sanc[i] = make_float4(fx, fy, fz, 0.f);   // no bound: scan again next time
-                    }
-                    cj[i] = bj;
                 }
+                bool exact = true;
+                if (k1 >= 0) {
+                    const float fb = face_distance(gv, bk, fx, fy, fz, eps);
+                    const float m2e = fminf(m2, fb * fb);
+                    const float tau = 16.f * (dl * sqrtf(m2e) * 1.001f + dl * dl + u * m2e);
+                    if ((nt == 1 && m2e == INFINITY) || (m2e - m1 > 2.f * tau && m2e < INFINITY)) {
+                        exact = false;
+                        bj = __float_as_int(ld_tgt<SH>(gv, k1).w);
+                        bd = exact_d2(x, y, z, bj);
+                        float rho = 0.f;
+                        if (m2e == INFINITY) rho = 1e30f;
+                        else if (m2e > 128.f * dl * dl && m2e - tau > 0.f) rho = sqrtf(m2e - tau) * 0.9999f;
+                        if (in_smem) sanc[i] = make_float4(fx, fy, fz, rho);
+                    }
+                }
+                if (exact) {
+                    count(4, 1);
+                    scan_block_exact(gv, bk, qx, qy, qz, x, y, z, fx, fy, fz, eps, bd, bj);
+                    if (in_smem) sanc[i] = make_float4(fx, fy, fz, 0.f);   // no bound: scan again next time
+                }
+                cj[i] = bj;
             }
             if (active && bj >= 0 && bd < p.r2) {
                 ++cnt;
@@ -539,7 +635,12 @@ icp_grid_kernel(const IcpParams p) {
         if (lane == 0) s_cnt[warp] = cnt;
     };
 
-    auto totals = [&](int w) -> int {
+    auto pass = [&](bool apply) __attribute__((always_inline)) {
+        if (grid_sh) pass_simple(apply, std::true_type{});
+        else pass_simple(apply, std::false_type{});
+    };
+
+    auto totals = [&](int w) __attribute__((always_inline)) -> int {
         if (lane < 16) {
             double t = s_part[0][lane];
 #pragma unroll
@@ -552,7 +653,7 @@ icp_grid_kernel(const IcpParams p) {
         __syncwarp();
         return c;
     };
-    auto cluster_totals = [&](int w) -> int {
+    auto cluster_totals = [&](int w) __attribute__((always_inline)) -> int {
         if (lane < 16) {
             double t = s_cl[0][lane];
 #pragma unroll
@@ -565,7 +666,7 @@ icp_grid_kernel(const IcpParams p) {
         __syncwarp();
         return c;
     };
-    auto cluster_publish = [&]() {
+    auto cluster_publish = [&]() __attribute__((always_inline)) {
         if constexpr (CS > 1) {
             cg::cluster_group cluster = cg::this_cluster();
             if (warp == 0) {
@@ -578,7 +679,7 @@ icp_grid_kernel(const IcpParams p) {
             cluster.sync();
         }
     };
-    auto cluster_fetch = [&]() {
+    auto cluster_fetch = [&]() __attribute__((always_inline)) {
         if constexpr (CS > 1) {
             cg::cluster_group cluster = cg::this_cluster();
             cluster.sync();
@@ -592,7 +693,7 @@ icp_grid_kernel(const IcpParams p) {
     };
 
     bool have_warm = false;
-    auto fit_pose = [&](int c) {
+    auto fit_pose = [&](int c) __attribute__((always_inline)) {
         const double *t = s_tot[0];
         double Um[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
         if (c > 0) {
@@ -630,7 +731,7 @@ icp_grid_kernel(const IcpParams p) {
     };
     // strict pose fit (warp 0, all lanes; CS == 1 only): the CPU reference's two-pass sums in ascending source
     // index, one accumulator per lane, then its Jacobi SVD on lane 0 (icp_common.cuh, namespace strict)
-    auto fit_strict = [&](int c) {
+    auto fit_strict = [&](int c) __attribute__((always_inline)) {
         double Um[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
         if (c > 0) {   // warp-uniform
             const double *src1 = lane == 0 ? px : (lane == 1 ? py : (lane == 2 ? pz : (lane == 3 ? qx : (lane == 4 ? qy : qz))));
@@ -671,7 +772,7 @@ icp_grid_kernel(const IcpParams p) {
             for (int k = 0; k < 12; ++k) s_U[k] = Um[k];
         }
     };
-    auto compose_pose = [&]() {
+    auto compose_pose = [&]() __attribute__((always_inline)) {
         double v = 0.0;
         if (lane < 16) {
             const int r = lane >> 2, cc = lane & 3;
@@ -685,13 +786,16 @@ icp_grid_kernel(const IcpParams p) {
     };
 
     // it = -1 is open3d's initial correspondence pass (no update applied)
+    const long long t_tile = dbg ? clock64() : 0;
     int iters = 0;
 #pragma unroll 1
     for (int it = -1; it < p.max_iter; ++it) {
         const bool apply = it >= 0;
         if (apply && rank == 0 && warp == kGW - 1) compose_pose();   // uses s_U of this iteration; next write is after barrier A
         pass(apply);
+        long long t_a = dbg ? clock64() : 0;
         __syncthreads();   // barrier A
+        if (dbg && tid == 0) { const long long t = clock64(); atomicAdd(dbg + 12, (unsigned long long)(t - t_a)); t_a = t; }
         cluster_publish();
         if (rank == 0) {
             if (warp == 0) {
@@ -713,12 +817,14 @@ icp_grid_kernel(const IcpParams p) {
         }
         cluster_fetch();
         __syncthreads();   // barrier B
+        if (dbg && tid == 0) atomicAdd(dbg + 13, (unsigned long long)(clock64() - t_a));
         if (apply) {
             iters = it + 1;
             if (s_stop) break;
         }
     }
     __syncthreads();
+    if (dbg && tid == 0) atomicMax(dbg + 14, (unsigned long long)(clock64() - t_tile));   // longest ICP loop of any CTA
 
     if (rank == 0 && tid == 0) {
         if (p.ori_only) {
@@ -741,21 +847,50 @@ icp_grid_kernel(const IcpParams p) {
     }
     if (rank == 0 && tid < 16) p.out_T[16 * (size_t)b + tid] = s_T[tid];
     const bool aff = s_T[12] == 0.0 && s_T[13] == 0.0 && s_T[14] == 0.0 && s_T[15] == 1.0;
-    for (int i = tid; i < ns; i += kGT) {
+    for (int t = tid; t < ns; t += kGT) {
+        const int i = in_smem ? sord[t] : t;   // slot -> point of the slice
+        const int j = cj[t];
+        // the winner belongs to the final position of the point (px is not moved after the last pass)
+        const bool inl = j >= 0 && exact_d2(px[t], py[t], pz[t], j) < p.r2;
         const size_t e = 3 * (size_t)(s0 + i);
         double x = ld_coord(p.src, p.pts_dtype, e), y = ld_coord(p.src, p.pts_dtype, e + 1),
                z = ld_coord(p.src, p.pts_dtype, e + 2);
         transform_point(s_T, aff, x, y, z);
         p.out_world[e] = x; p.out_world[e + 1] = y; p.out_world[e + 2] = z;
-        const int j = cj[i];
-        // the winner belongs to the final position of the point (px is not moved after the last pass)
-        const bool inl = j >= 0 && exact_d2(px[i], py[i], pz[i], j) < p.r2;
         p.out_corr[s0 + i] = inl ? __ldg(p.qi + q0 + j) : -1;
     }
 }
 
+// CS > 1: one cluster per tile.  CS == 1: persistent CTAs (one per SM) take tiles from a queue, so a sweep whose
+// tiles all belong to the small-tile kernel costs one CTA per SM walking the tile table, not a grid of n_tiles
+// CTAs with 100+ KB of shared memory each.
+template <int CS>
+__global__ void __launch_bounds__(kGT, 1)
+icp_grid_kernel(const IcpParams p) {
+    if constexpr (CS > 1) {
+        grid_tile<CS>(p, (int)(blockIdx.x / CS));
+    } else {
+        __shared__ int s_next;
+        for (;;) {
+            __syncthreads();   // the previous tile is completely done (shared memory is reused)
+            if (threadIdx.x == 0) {
+                // skip the tiles other kernels own without a block-wide round trip each
+                int b = atomicAdd(p.queue2, 1);
+                while (b < p.n_tiles && !tile_uses_grid(p, p.src_off[b + 1] - p.src_off[b], p.cnt[b])) b = atomicAdd(p.queue2, 1);
+                s_next = b;
+            }
+            __syncthreads();
+            const int b = s_next;
+            if (b >= p.n_tiles) return;
+            grid_tile<1>(p, b);
+        }
+    }
+}
+
+// per source point: anchor, position, winner, slot -> point index
+constexpr size_t kGridBytesPerPoint = sizeof(float4) + 3 * sizeof(double) + 2 * sizeof(int);
 size_t icp_grid_smem_bytes(int pcap, int grid_bytes) {
-    return (size_t)pcap * (sizeof(float4) + 3 * sizeof(double) + sizeof(int)) + (size_t)grid_bytes;
+    return (size_t)pcap * kGridBytesPerPoint + (size_t)kGridSortMax * sizeof(unsigned) + (size_t)grid_bytes;
 }
 
 int launch_icp_grid(const IcpParams &P, int n_tiles, cudaStream_t stream) {
@@ -780,7 +915,10 @@ int launch_icp_grid(const IcpParams &P, int n_tiles, cudaStream_t stream) {
     } else {
         if (smem > 32 * 1024)
             AURDF_CUDA_CHECK(cudaFuncSetAttribute(icp_grid_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        icp_grid_kernel<1><<<n_tiles, kGT, smem, stream>>>(P);
+        int dev = 0, sms = kNumSMs;
+        AURDF_CUDA_CHECK(cudaGetDevice(&dev));
+        AURDF_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        icp_grid_kernel<1><<<n_tiles < sms ? n_tiles : sms, kGT, smem, stream>>>(P);
     }
     return AURDF_OK;
 }

@@ -38,7 +38,7 @@ constexpr int kIcpWarps = kIcpThreads / 32;
 constexpr int kQChunk = 1024;     // target points staged per shared-memory chunk (24 KB f64 SoA + 16 KB float4)
 constexpr int kClusterCtas = 8;   // CTAs per tile in the cluster variant (large tiles)
 constexpr int kPSmemMax = 2048;   // most source points a tile may keep in shared memory
-constexpr int kGridPcapMax = 2048; // most source points a CTA of the grid kernel keeps in shared memory (44 B each)
+constexpr int kGridPcapMax = 2048; // most source points a CTA of the grid kernel keeps in shared memory (48 B each)
 
 struct WsLayout {
     size_t box, cnt, toff, qx, qy, qz, qi, pspill, status, gs, gends, gpar, total;
@@ -55,7 +55,7 @@ static WsLayout make_layout(int64_t B, int64_t total_src, int64_t cap) {
     L.box = take((size_t)B * 6 * sizeof(double));
     L.cnt = take((size_t)B * sizeof(int));
     L.toff = take((size_t)(B + 1) * sizeof(long long));
-    L.status = take(4 * sizeof(int));
+    L.status = take(8 * sizeof(int));
     L.qx = take((size_t)cap * sizeof(double));
     L.qy = take((size_t)cap * sizeof(double));
     L.qz = take((size_t)cap * sizeof(double));
@@ -214,6 +214,7 @@ tile_scan_kernel(const int *__restrict__ cnt, int B, long long capacity, long lo
         status_int[1] = (int)(total & 0xffffffffLL);
         status_int[2] = (int)(total >> 32);
         status_int[3] = 0;   // tile queue of the small-tile kernel
+        status_int[4] = 0;   // tile queue of the grid kernel
         if (status_user) {
             status_user[0] = over;
             status_user[1] = status_int[1];
@@ -863,7 +864,7 @@ static const Tuning &tuning() {
         v.strict_nt = geti("AURDF_ICP_STRICT_NT", 16);
         v.grid = geti("AURDF_ICP_GRID", 1);
         v.grid_cs_ns = geti("AURDF_ICP_GRID_CS_NS", 1024);
-        v.grid_smem_kb = geti("AURDF_ICP_GRID_SMEM_KB", 64);
+        v.grid_smem_kb = geti("AURDF_ICP_GRID_SMEM_KB", 112);
         return v;
     }();
     return t;
@@ -990,6 +991,7 @@ extern "C" int aurdf_icp_sweep(const void *src_xyz, int pts_dtype, const int32_t
     P.small_nt = kSmNt32;
     P.n_tiles = n_tiles;
     P.queue = status_int + 3;
+    P.queue2 = status_int + 4;
     P.strict_nt = tn.strict_nt;
     // grid-pruned search for the tiles the small-tile kernel does not take: one CTA per tile, or an 8-CTA
     // cluster when the caller announces tiles of more than grid_cs_ns source points
@@ -998,9 +1000,9 @@ extern "C" int aurdf_icp_sweep(const void *src_xyz, int pts_dtype, const int32_t
     P.grid_pcap = ((max_src_per_tile > 0 ? max_src_per_tile : 256) + P.grid_cs - 1) / P.grid_cs;
     if (P.grid_pcap > kGridPcapMax) P.grid_pcap = kGridPcapMax;
     P.grid_pcap = (P.grid_pcap + 3) & ~3;
-    // one CTA per tile: 64 KB for the grid (n_t <= ~3200) keeps two CTAs per SM; cluster variant (few, large
+    // one CTA (512 threads, the whole register file) per tile and SM: 112 KB for the grid (n_t <= ~5700); cluster variant (few, large
     // tiles): whatever one CTA per SM leaves after the source-point state and the static arrays
-    P.grid_smem_bytes = P.grid_cs == 1 ? tn.grid_smem_kb * 1024 : (227 - 4) * 1024 - P.grid_pcap * 44;
+    P.grid_smem_bytes = P.grid_cs == 1 ? tn.grid_smem_kb * 1024 : (227 - 4) * 1024 - P.grid_pcap * 48 - 2048 * 4;
     if (P.grid_smem_bytes < 0) P.grid_smem_bytes = 0;
     P.gs = (float4 *)(ws + L.gs); P.gends = (int *)(ws + L.gends); P.gpar = (float *)(ws + L.gpar);
     EvPair ev{nullptr, nullptr};

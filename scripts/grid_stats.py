@@ -16,14 +16,22 @@ run = lambda: ci.icp_sweep(d["src"], d["src_off"], d["tgt"], d["tgt_off"], d["ti
                            max_src_per_tile=int(np.diff(b.src_off).max()))
 r = run(); torch.cuda.synchronize()
 lib.aurdf_debug_set_clock_buffer(buf.data_ptr())
+buf[15] = 1                                   # counters
 r = run(); torch.cuda.synchronize()
+c = buf.cpu().numpy()[:16].copy()
+buf.zero_(); buf[15] = 2                      # phase timers (separately: the counters' atomics distort them)
+r = run(); torch.cuda.synchronize()
+c[6:15] = buf.cpu().numpy()[6:15]
 lib.aurdf_debug_set_clock_buffer(None)
-c = buf.cpu().numpy()[:6]
 it = r.iters.cpu().numpy(); nt = r.ntgt.cpu().numpy(); ns = np.diff(b.src_off)
 print(f"C5 {n}x{k}: {b.n_tiles} tiles, mean n_s {ns.mean():.0f}, mean n_t {nt.mean():.0f}, iters mean {it.mean():.1f} max {it.max()}")
 print(f"queries {c[0]}, cache hits {c[1]} ({100*c[1]/max(c[0],1):.1f} %), block scans {c[2]} ({c[2]/max(c[0]-c[1],1):.2f} per miss), "
       f"candidates per scan {c[3]/max(c[2],1):.1f} (brute force: {nt.mean():.0f}), exact fallbacks {c[4]} ({100*c[4]/max(c[0],1):.3f} %), "
       f"whole-grid scans {c[5]} ({100*c[5]/max(c[2],1):.2f} %)")
+passes = max(c[7], 1)
+print(f"per pass (thread 0 of every CTA, cycles): move+cache test {c[8]/passes:.0f}, item generation {c[9]/passes:.0f}, item scan {c[10]/passes:.0f}, "
+      f"per-query finish {c[11]/passes:.0f}, wait at barrier A {c[12]/passes:.0f}, fit + barrier B {c[13]/passes:.0f}")
+print(f"longest ICP loop of a CTA: {c[14]} cycles = {c[14]/max(int(it.max())+1,1):.0f} per pass if it is the {it.max()}-iteration tile")
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 plan = ci.IcpSweep(b.n_tiles, b.src.shape[0], r.needed_capacity() + 64, int(ns.max()))
 f = lambda: plan.run(d["src"], d["src_off"], d["tgt"], d["tgt_off"], d["tile_frame"], d["box"], d["box_off"], d["init_T"])
