@@ -31,6 +31,11 @@ constexpr int kNumSMs = 148;  // B200
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+// current device and its SM count (cached per device; idempotent, so the unsynchronised fill is benign)
+int current_device_sms(int *device);
+// run `set` once per (slot, device): kernel attributes that never change (idempotent as well)
+bool once_per_device(int slot, int device);
+
 // ---- storage-dtype-agnostic coordinate load (exact widening of float32) -------------------
 __device__ __forceinline__ double ld_coord(const void *base, int dtype, size_t idx) {
     return dtype == AURDF_F32 ? (double)__ldg((const float *)base + idx) : __ldg((const double *)base + idx);

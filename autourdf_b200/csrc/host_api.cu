@@ -39,10 +39,6 @@ struct aurdf_ctx {
     std::mutex lock;
 };
 
-namespace aurdf {
-void set_concurrent_sweeps(int n);   // icp_sweep.cu
-}
-
 namespace {
 using aurdf::align_up;
 
@@ -281,7 +277,6 @@ static int sweep_host_locked(aurdf_ctx *c, const void *src_xyz, int pts_dtype, c
         // per-tile arrays are shifted to the chunk's first tile; point arrays keep their base because the
         // offsets stored in src_off / box_off / tgt_off are global
         const Blk &B = blk[k];
-        aurdf::set_concurrent_sweeps(n_chunks);   // frame blocks run as concurrent launches: residency for all of them
         rc2 = aurdf_icp_sweep(di + o_src, pts_dtype, (const int32_t *)(di + o_soff) + q.t0, di + o_tgt,
                               (const int32_t *)(di + o_toff), (const int32_t *)(di + o_tf) + q.t0,
                               box_xyz ? (const void *)(di + o_box) : nullptr, box_dtype,
@@ -292,7 +287,6 @@ static int sweep_host_locked(aurdf_ctx *c, const void *src_xyz, int pts_dtype, c
                               (double *)(d_o + B.fit), (double *)(d_o + B.rmse), (int32_t *)(d_o + B.it),
                               (int32_t *)(d_o + B.nt), (char *)c->d_ws + q.ws_off, q.ws_bytes, q.cap,
                               (int32_t *)(d_o + B.status), st);
-        aurdf::set_concurrent_sweeps(1);
         if (rc2 != AURDF_OK) return rc2;
         // optimistic: queue the status and every output behind the kernels; if the capacity guess was
         // too small the chunk is simply run again (inputs already resident)
@@ -355,7 +349,9 @@ static int sweep_host_locked(aurdf_ctx *c, const void *src_xyz, int pts_dtype, c
             }
             need = (int64_t)(uint32_t)st[1] | ((int64_t)st[2] << 32);
         }
-        c->cap_hint[k] = need + need / 8 + 64;   // next call of the same shape fits first time
+        // next call of the same shape fits first time; never shrinks: the frames of a sequence alternate between
+        // needs, and a too-small guess costs a second run (plus, if the workspace must grow, a cudaMalloc)
+        if (need + need / 8 + 64 > c->cap_hint[k]) c->cap_hint[k] = need + need / 8 + 64;
         // unpack this block's per-tile outputs while the later blocks are still running
         const size_t n = (size_t)(ch[k].t1 - ch[k].t0), t0 = (size_t)ch[k].t0;
         memcpy(out_T + 16 * t0, ho + blk[k].T, n * 16 * 8);

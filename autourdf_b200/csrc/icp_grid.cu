@@ -896,9 +896,12 @@ size_t icp_grid_smem_bytes(int pcap, int grid_bytes) {
 int launch_icp_grid(const IcpParams &P, int n_tiles, cudaStream_t stream) {
     if (P.grid_cs > 1) grid_build_kernel<<<n_tiles, kGT, 0, stream>>>(P);   // CS == 1 builds its grid in the ICP kernel
     const size_t smem = icp_grid_smem_bytes(P.grid_pcap, P.grid_smem_bytes);
+    int dev = 0;
+    const int sms = current_device_sms(&dev);
+    // opt-in ceilings: 227 KB per CTA minus the static arrays of each variant
     if (P.grid_cs > 1) {
-        if (smem > 32 * 1024)
-            AURDF_CUDA_CHECK(cudaFuncSetAttribute(icp_grid_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (once_per_device(2, dev))
+            AURDF_CUDA_CHECK(cudaFuncSetAttribute(icp_grid_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 223 * 1024));
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3((unsigned)n_tiles * 8);
         cfg.blockDim = dim3(kGT);
@@ -913,11 +916,8 @@ int launch_icp_grid(const IcpParams &P, int n_tiles, cudaStream_t stream) {
         cfg.numAttrs = 1;
         AURDF_CUDA_CHECK(cudaLaunchKernelEx(&cfg, icp_grid_kernel<8>, P));
     } else {
-        if (smem > 32 * 1024)
-            AURDF_CUDA_CHECK(cudaFuncSetAttribute(icp_grid_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        int dev = 0, sms = kNumSMs;
-        AURDF_CUDA_CHECK(cudaGetDevice(&dev));
-        AURDF_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        if (once_per_device(3, dev))
+            AURDF_CUDA_CHECK(cudaFuncSetAttribute(icp_grid_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 221 * 1024));
         icp_grid_kernel<1><<<n_tiles < sms ? n_tiles : sms, kGT, smem, stream>>>(P);
     }
     return AURDF_OK;

@@ -635,11 +635,11 @@ icp_small2_kernel(const IcpParams p) {
 // host side: persistent CTAs, MINB per SM, tiles from the queue
 template <int MINB, bool DBG>
 static int launch_variant2(const IcpParams &P, int n_tiles, cudaStream_t stream) {
-    int dev = 0, sms = kNumSMs;
-    AURDF_CUDA_CHECK(cudaGetDevice(&dev));
-    AURDF_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    // MINB x (35.3 KB + static) per SM only fits with the carve-out at its maximum (idempotent, per device)
-    AURDF_CUDA_CHECK(cudaFuncSetAttribute(icp_small2_kernel<MINB, DBG>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    int dev = 0;
+    const int sms = current_device_sms(&dev);
+    // MINB x (35.3 KB + static) per SM only fits with the carve-out at its maximum (set once per device and variant)
+    if (once_per_device(4 + MINB + (DBG ? 4 : 0), dev))
+        AURDF_CUDA_CHECK(cudaFuncSetAttribute(icp_small2_kernel<MINB, DBG>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     const int grid = n_tiles < sms * MINB ? n_tiles : sms * MINB;
     icp_small2_kernel<MINB, DBG><<<grid, kNT, kSmall2SmemBytes, stream>>>(P);
     return AURDF_OK;

@@ -859,7 +859,7 @@ static const Tuning &tuning() {
         };
         Tuning v;
         v.small = geti("AURDF_ICP_SMALL", 2);
-        v.minb = geti("AURDF_ICP_SMALL_MINB", 0);   // 0: chosen per call, see small_tile_residency()
+        v.minb = geti("AURDF_ICP_SMALL_MINB", 4);
         v.split = geti("AURDF_ICP_SMALL_SPLIT", 1);
         v.strict_nt = geti("AURDF_ICP_STRICT_NT", 16);
         v.grid = geti("AURDF_ICP_GRID", 1);
@@ -870,18 +870,12 @@ static const Tuning &tuning() {
     return t;
 }
 
-// Residency the small-tile kernel is compiled for.  Measured (profiles/r02_notes.md): one launch per step runs
-// fastest with 4 CTAs per SM (122 registers, no spills; the launch is bound by its slowest tile, not by
-// occupancy); the host path, whose frame blocks run as concurrent launches on separate streams, with 6 (every
-// tile of every block resident at once).
-static thread_local int g_concurrent_sweeps = 1;
-namespace aurdf {
-void set_concurrent_sweeps(int n) { g_concurrent_sweeps = n > 0 ? n : 1; }
-}
+// Residency the small-tile kernel is compiled for: 4 CTAs per SM (122 registers, no spills).  The launch is bound by
+// its slowest tile and by instruction issue, not by occupancy: measured on wx200_5 / franka / allegro_hand, 4 beats
+// 5 and 6 both device-resident and through the host path (profiles/r02_notes.md).
 static int small_tile_residency() {
     const int forced = tuning().minb;
-    if (forced >= 4 && forced <= 6) return forced;
-    return g_concurrent_sweeps > 1 ? 6 : 4;
+    return forced >= 4 && forced <= 6 ? forced : 4;
 }
 
 extern "C" int aurdf_icp_sweep_launches(void) { return tuning().small ? 5 : 4; }

@@ -10,8 +10,8 @@ A "step" is one pass of the hot path over the wx200_5 workload (C2: 5 sequences 
 reference's convergence rule.  Synthetic data (autourdf_b200.synth), float64 arithmetic.
 
   value     frames/s with inputs resident in HBM (CUDA events, max over ranks, L2 flushed
-            between steps); at N GPUs every rank sweeps its own sequences (weak scaling)
-            and the fitted poses are all-gathered over NCCL inside the timed region
+            between steps); at N GPUs every rank sweeps one wx200_5 batch (weak scaling: per-GPU
+            work fixed) and the fitted poses are all-gathered over NCCL inside the timed region
   e2e       the same through the host-buffer C-ABI call (aurdf_icp_sweep_host): numpy in,
             numpy out, H2D + D2H copies inside the timed region (the call cuts the batch into
             three frame blocks on separate streams so copies and kernels overlap)
@@ -137,7 +137,7 @@ def config_dict(b, name, scaling, world):
             "clusters": b.n_clusters, "tiles_per_step" + per: b.n_tiles,
             "l2": "flushed between steps (256 MiB write) on the GPU arm",
             "parallelism": (f"one {name} batch sharded by frame blocks over {world} GPU(s)" if scaling == "strong" else
-                            f"every GPU sweeps its own {name} sequences ({world} GPU(s))") + ", one all-gather of poses"}
+                            f"every GPU sweeps one {name} batch ({world} GPU(s))") + ", one all-gather of poses"}
 
 
 def finish(world, line=None):
@@ -245,7 +245,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
-                    help="weak (default, the driver's contract): every GPU sweeps its own sequences; strong: ONE "
+                    help="weak (default, the driver's contract): every GPU sweeps one batch of --workload; strong: ONE "
                          "batch of --workload sharded over the GPUs by frame blocks (autourdf_b200.dist.ShardedSweep)")
     ap.add_argument("--workload", default=WORKLOAD)
     args = ap.parse_args()
@@ -271,8 +271,12 @@ def main():
     L = _lib.lib()
     strong = args.scaling == "strong"
 
-    # weak: this rank's own sequences; strong: the same batch on every rank, of which it keeps its share
-    b_all = make_workload(0 if strong else rank, args.workload)
+    # weak: every rank sweeps the SAME batch (per-GPU work exactly fixed as N grows, the definition of weak scaling;
+    # ICP work is data-dependent, so per-rank seeds would give every rank a different amount of work --
+    # AURDF_BENCH_RANK_SEEDS=1 selects that variant, profiles/r02_scaling.md has both); strong: the same batch on
+    # every rank, of which it keeps its share
+    rank_seeds = os.environ.get("AURDF_BENCH_RANK_SEEDS") == "1"
+    b_all = make_workload(rank if (rank_seeds and not strong) else 0, args.workload)
     sharded = None
     if strong:
         from autourdf_b200.dist import ShardedSweep

@@ -14,6 +14,7 @@ run() {   # name, extra args...
   grep '^{' gpurun_out/${TAG}_scale_${name}_$N.json | tail -1 | python -c "import json,sys; d=json.loads(sys.stdin.read()); print({k: d[k] for k in ('value','ms_per_step','n_gpus','scaling')}, d['e2e']['value'], d['detail'])"
 }
 run weak
+AURDF_BENCH_RANK_SEEDS=1 run weak_rank_seeds
 run strong_allegro --scaling strong --workload allegro_hand
 run strong_c5 --scaling strong --workload c5:16384x128x40
 NCCL_DEBUG=INFO run weak_nccl_info
