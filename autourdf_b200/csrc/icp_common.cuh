@@ -570,6 +570,7 @@ struct IcpParams {
     int n_tiles;
     int *queue;            // small-tile kernel v2: next tile to take (zeroed by tile_scan_kernel)
     int *queue2;           // grid kernel, one-CTA variant: its own tile queue (zeroed by tile_scan_kernel)
+    int *glist;            // workspace: the tiles the grid kernel owns (written by tile_scan_kernel, count in status_int[5])
     int strict_nt;         // tiles with at most this many masked targets fit their poses in strict mode
     // grid-pruned search (icp_grid.cu): medium / large tiles
     int grid_on;           // 0: every non-small tile runs in the brute-force general kernel

@@ -874,10 +874,8 @@ icp_grid_kernel(const IcpParams p) {
         for (;;) {
             __syncthreads();   // the previous tile is completely done (shared memory is reused)
             if (threadIdx.x == 0) {
-                // skip the tiles other kernels own without a block-wide round trip each
-                int b = atomicAdd(p.queue2, 1);
-                while (b < p.n_tiles && !tile_uses_grid(p, p.src_off[b + 1] - p.src_off[b], p.cnt[b])) b = atomicAdd(p.queue2, 1);
-                s_next = b;
+                const int k = atomicAdd(p.queue2, 1);   // position in the list tile_scan_kernel made of this kernel's tiles
+                s_next = k < p.status_int[5] ? p.glist[k] : p.n_tiles;
             }
             __syncthreads();
             const int b = s_next;

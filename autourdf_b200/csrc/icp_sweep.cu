@@ -41,7 +41,7 @@ constexpr int kPSmemMax = 2048;   // most source points a tile may keep in share
 constexpr int kGridPcapMax = 2048; // most source points a CTA of the grid kernel keeps in shared memory (48 B each)
 
 struct WsLayout {
-    size_t box, cnt, toff, qx, qy, qz, qi, pspill, status, gs, gends, gpar, total;
+    size_t box, cnt, toff, qx, qy, qz, qi, pspill, status, gs, gends, gpar, glist, total;
 };
 
 static WsLayout make_layout(int64_t B, int64_t total_src, int64_t cap) {
@@ -64,6 +64,7 @@ static WsLayout make_layout(int64_t B, int64_t total_src, int64_t cap) {
     L.gs = take((size_t)cap * sizeof(float4));
     L.gends = take((size_t)(cap + 2 * B + 2) * sizeof(int));
     L.gpar = take((size_t)B * 8 * sizeof(float));
+    L.glist = take((size_t)B * sizeof(int));
     L.total = o;
     return L;
 }
@@ -172,9 +173,11 @@ box_count_kernel(const void *__restrict__ box_xyz, int box_dtype, const int *__r
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024)
 tile_scan_kernel(const int *__restrict__ cnt, int B, long long capacity, long long *__restrict__ toff,
-                 int *__restrict__ status_int, int *__restrict__ status_user) {
+                 int *__restrict__ status_int, int *__restrict__ status_user, const IcpParams P) {
     __shared__ long long s_warp[32];
     __shared__ long long s_carry;
+    __shared__ int s_wc[32];
+    __shared__ int s_gbase;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) s_carry = 0;
     __syncthreads();
@@ -206,7 +209,30 @@ tile_scan_kernel(const int *__restrict__ cnt, int B, long long capacity, long lo
         if (tid == 1023) s_carry = excl + v;
         __syncthreads();
     }
+    // the tiles the grid kernel owns, in tile order: its persistent CTAs take them from this list, so a sweep of
+    // small tiles costs them one atomic each instead of a walk over the tile table
+    if (tid == 0) s_gbase = 0;
+    __syncthreads();
+    for (int base = 0; base < B; base += 1024) {
+        const int i = base + tid;
+        const bool g = i < B && tile_uses_grid(P, P.src_off[i + 1] - P.src_off[i], cnt[i]);
+        const unsigned bal = __ballot_sync(0xffffffffu, g);
+        if (lane == 0) s_wc[warp] = __popc(bal);
+        __syncthreads();
+        int before = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < 32; ++w) {
+            const int c = s_wc[w];
+            before += w < warp ? c : 0;
+            total += c;
+        }
+        if (g) P.glist[s_gbase + before + __popc(bal & ((1u << lane) - 1u))] = i;
+        __syncthreads();
+        if (tid == 0) s_gbase += total;
+        __syncthreads();
+    }
     if (tid == 0) {
+        status_int[5] = s_gbase;   // number of listed tiles
         long long total = s_carry;
         toff[B] = total;
         int over = total > capacity ? 1 : 0;
@@ -964,11 +990,6 @@ extern "C" int aurdf_icp_sweep(const void *src_xyz, int pts_dtype, const int32_t
             AURDF_CUDA_CHECK(cudaFuncSetAttribute(icp_tiles_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     }
 
-    box_count_kernel<<<n_tiles, kIcpThreads, 0, stream>>>(box_xyz, box_dtype, box_off, tgt_xyz, pts_dtype, tgt_off,
-                                                          tile_frame, box_scale, box, cnt);
-    tile_scan_kernel<<<1, 1024, 0, stream>>>(cnt, n_tiles, (long long)tgt_capacity, toff, status_int, status);
-    mask_fill_kernel<<<n_tiles, kIcpThreads, 0, stream>>>(tgt_xyz, pts_dtype, tgt_off, tile_frame, box, toff,
-                                                          status_int, qx, qy, qz, qi);
     IcpParams P;
     P.src = src_xyz; P.pts_dtype = pts_dtype; P.src_off = src_off; P.init_T = init_T;
     P.r2 = max_corr_dist * max_corr_dist; P.max_iter = max_iter; P.rel_fit = rel_fitness; P.rel_rmse = rel_rmse;
@@ -999,6 +1020,12 @@ extern "C" int aurdf_icp_sweep(const void *src_xyz, int pts_dtype, const int32_t
     P.grid_smem_bytes = P.grid_cs == 1 ? tn.grid_smem_kb * 1024 : (227 - 4) * 1024 - P.grid_pcap * 48 - 2048 * 4;
     if (P.grid_smem_bytes < 0) P.grid_smem_bytes = 0;
     P.gs = (float4 *)(ws + L.gs); P.gends = (int *)(ws + L.gends); P.gpar = (float *)(ws + L.gpar);
+    P.glist = (int *)(ws + L.glist);
+    box_count_kernel<<<n_tiles, kIcpThreads, 0, stream>>>(box_xyz, box_dtype, box_off, tgt_xyz, pts_dtype, tgt_off,
+                                                          tile_frame, box_scale, box, cnt);
+    tile_scan_kernel<<<1, 1024, 0, stream>>>(cnt, n_tiles, (long long)tgt_capacity, toff, status_int, status, P);
+    mask_fill_kernel<<<n_tiles, kIcpThreads, 0, stream>>>(tgt_xyz, pts_dtype, tgt_off, tile_frame, box, toff,
+                                                          status_int, qx, qy, qz, qi);
     EvPair ev{nullptr, nullptr};
     if (g_prof_on) {
         AURDF_CUDA_CHECK(cudaEventCreate(&ev.a));
