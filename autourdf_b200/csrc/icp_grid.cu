@@ -369,6 +369,7 @@ __device__ __forceinline__ void grid_tile(const IcpParams &p, const int b) {
     const int ns_tile = p.src_off[b + 1] - p.src_off[b];
     const int nt = p.cnt[b];
     if (!tile_uses_grid(p, ns_tile, nt)) return;   // another kernel owns this tile (the whole cluster leaves)
+    if constexpr (CS > 1) cg::this_cluster().sync();   // every CTA of the cluster runs before any touches a peer's shared memory
     // CS == 1 owns every tile the small-tile kernel leaves, rank-deficient ones included (strict pose fit)
     const bool strict_tile = nt <= p.strict_nt;
     const int per = (ns_tile + CS - 1) / CS;

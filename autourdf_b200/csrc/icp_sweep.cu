@@ -360,6 +360,7 @@ icp_tiles_kernel(const IcpParams p) {
     const int nt = p.cnt[b];
     const long long q0 = p.toff[b];
     if (tile_uses_small(p, ns_tile, nt) || tile_uses_grid(p, ns_tile, nt)) return;   // another kernel owns this tile (whole cluster leaves)
+    if constexpr (CS > 1) cg::this_cluster().sync();   // every CTA of the cluster runs before any touches a peer's shared memory
     const bool resident = nt <= kQChunk;
     const int nchunks = (nt + kQChunk - 1) / kQChunk;
 
