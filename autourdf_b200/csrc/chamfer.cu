@@ -320,6 +320,7 @@ extern "C" int aurdf_nn_f32(const float *query_xyz, const int32_t *query_off, co
                             const int32_t *target_off, int32_t n_groups, int64_t n_queries, int64_t n_targets, int norm,
                             int32_t *out_idx, float *out_dist, void *workspace, size_t workspace_bytes,
                             aurdf_stream_t stream_) {
+    aurdf::NvtxRange nvtx_range("aurdf_nn_f32");
     cudaStream_t stream = (cudaStream_t)stream_;
     AURDF_REQUIRE(n_groups >= 0 && n_queries >= 0 && n_targets >= 0, "aurdf_nn_f32: negative size");
     AURDF_REQUIRE(norm == 1 || norm == 2, "aurdf_nn_f32: norm must be 1 or 2");
@@ -354,6 +355,7 @@ extern "C" int aurdf_nn_f32(const float *query_xyz, const int32_t *query_off, co
 extern "C" int aurdf_nn_f32_bwd(const float *p1_xyz, const int32_t *p1_off, const float *p2_xyz, const int32_t *p2_off,
                                 const int32_t *idx, const float *grad_dist, int32_t n_groups, int64_t n_p1, int norm,
                                 float *grad_p1, float *grad_p2, aurdf_stream_t stream_) {
+    aurdf::NvtxRange nvtx_range("aurdf_nn_f32_bwd");
     cudaStream_t stream = (cudaStream_t)stream_;
     AURDF_REQUIRE(n_groups >= 0 && n_p1 >= 0, "aurdf_nn_f32_bwd: negative size");
     AURDF_REQUIRE(norm == 1 || norm == 2, "aurdf_nn_f32_bwd: norm must be 1 or 2");
@@ -385,6 +387,7 @@ static void chamfer_weights(int N, int P1, int P2, int point_mean, int batch_mea
 extern "C" int aurdf_chamfer_fwd(const float *x, const float *y, int32_t N, int32_t P1, int32_t P2, int norm, int point_mean,
                                  int batch_mean, int32_t *idx_x, int32_t *idx_y, float *loss, void *workspace,
                                  size_t workspace_bytes, aurdf_stream_t stream_) {
+    aurdf::NvtxRange nvtx_range("aurdf_chamfer_fwd");
     cudaStream_t stream = (cudaStream_t)stream_;
     AURDF_REQUIRE(N > 0 && P1 > 0 && P2 > 0, "aurdf_chamfer_fwd: empty batch or cloud");
     AURDF_REQUIRE(norm == 1 || norm == 2, "aurdf_chamfer_fwd: norm must be 1 or 2");
@@ -415,6 +418,7 @@ extern "C" int aurdf_chamfer_fwd(const float *x, const float *y, int32_t N, int3
 extern "C" int aurdf_chamfer_bwd(const float *x, const float *y, const int32_t *idx_x, const int32_t *idx_y,
                                  const float *grad_loss, int32_t N, int32_t P1, int32_t P2, int norm, int point_mean,
                                  int batch_mean, float *grad_x, float *grad_y, aurdf_stream_t stream_) {
+    aurdf::NvtxRange nvtx_range("aurdf_chamfer_bwd");
     cudaStream_t stream = (cudaStream_t)stream_;
     AURDF_REQUIRE(N > 0 && P1 > 0 && P2 > 0, "aurdf_chamfer_bwd: empty batch or cloud");
     AURDF_REQUIRE(norm == 1 || norm == 2, "aurdf_chamfer_bwd: norm must be 1 or 2");

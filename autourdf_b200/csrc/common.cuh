@@ -5,6 +5,8 @@
 #include <math.h>
 #include <stdint.h>
 
+#include <nvtx3/nvToolsExt.h>   // header-only NVTX v3: ranges show up in nsys / ncu timelines, cost nothing without a tool
+
 #include "aurdf.h"
 
 namespace aurdf {
@@ -28,6 +30,14 @@ int cuda_fail(cudaError_t e, const char *what);
     } while (0)
 
 constexpr int kNumSMs = 148;  // B200
+
+// NVTX range over a C-ABI entry point (tracing)
+struct NvtxRange {
+    explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+    NvtxRange(const NvtxRange &) = delete;
+    NvtxRange &operator=(const NvtxRange &) = delete;
+};
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 

@@ -330,6 +330,7 @@ static bool dq_two_out(int op) { return dq_shape(op).o1 > 0; }
 
 extern "C" int aurdf_dq_op(int op, const void *in0, const void *in1, void *out0, void *out1, int64_t n, int dtype,
                            aurdf_stream_t stream_) {
+    aurdf::NvtxRange nvtx_range("aurdf_dq_op");
     cudaStream_t stream = (cudaStream_t)stream_;
     AURDF_REQUIRE(op >= 0 && op <= AURDF_MATRIX_TO_Q, "aurdf_dq_op: unknown op");
     AURDF_REQUIRE(n >= 0, "aurdf_dq_op: n < 0");
@@ -347,6 +348,7 @@ extern "C" int aurdf_dq_op(int op, const void *in0, const void *in1, void *out0,
 
 extern "C" int aurdf_dq_op_bwd(int op, const void *in0, const void *in1, const void *gout0, const void *gout1, void *gin0,
                                void *gin1, int64_t n, int dtype, aurdf_stream_t stream_) {
+    aurdf::NvtxRange nvtx_range("aurdf_dq_op_bwd");
     cudaStream_t stream = (cudaStream_t)stream_;
     AURDF_REQUIRE(op >= 0 && op <= AURDF_MATRIX_TO_Q, "aurdf_dq_op_bwd: unknown op");
     AURDF_REQUIRE(n >= 0, "aurdf_dq_op_bwd: n < 0");

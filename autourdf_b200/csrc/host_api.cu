@@ -372,6 +372,7 @@ extern "C" int aurdf_icp_sweep_host(aurdf_ctx *c, const void *src_xyz, int pts_d
                                     int32_t max_iter, double rel_fitness, double rel_rmse, int32_t ori_only,
                                     double *out_T, double *out_world_xyz, int32_t *out_corr, double *out_fitness,
                                     double *out_rmse, int32_t *out_iters, int32_t *out_ntgt) {
+    aurdf::NvtxRange nvtx_range("aurdf_icp_sweep_host");
     AURDF_REQUIRE(c != nullptr, "aurdf_icp_sweep_host: NULL ctx");
     AURDF_REQUIRE(n_tiles >= 0 && n_frames >= 0, "aurdf_icp_sweep_host: negative size");
     std::lock_guard<std::mutex> guard(c->lock);

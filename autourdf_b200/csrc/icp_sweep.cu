@@ -945,6 +945,7 @@ extern "C" int aurdf_icp_sweep(const void *src_xyz, int pts_dtype, const int32_t
                                double *out_world_xyz, int32_t *out_corr, double *out_fitness, double *out_rmse,
                                int32_t *out_iters, int32_t *out_ntgt, void *workspace, size_t workspace_bytes,
                                int64_t tgt_capacity, int32_t *status, aurdf_stream_t stream_) {
+    aurdf::NvtxRange nvtx_range("aurdf_icp_sweep");
     cudaStream_t stream = (cudaStream_t)stream_;
     AURDF_REQUIRE(n_tiles >= 0, "aurdf_icp_sweep: n_tiles < 0");
     if (n_tiles == 0) return AURDF_OK;

@@ -166,6 +166,7 @@ extern "C" size_t aurdf_coord_dist_map_workspace_bytes(int32_t n_frames, int32_t
 extern "C" int aurdf_coord_dist_map(const double *matrices, int32_t n_frames, int32_t n_coords, double bounding_box,
                                     int32_t diff, double *out_map, double *out_sum, void *workspace,
                                     size_t workspace_bytes, aurdf_stream_t stream_) {
+    aurdf::NvtxRange nvtx_range("aurdf_coord_dist_map");
     cudaStream_t stream = (cudaStream_t)stream_;
     AURDF_REQUIRE(n_frames >= 0 && n_coords >= 0, "aurdf_coord_dist_map: negative size");
     AURDF_REQUIRE(n_coords <= kMapMaxK, "aurdf_coord_dist_map: more than 384 clusters");

@@ -63,6 +63,7 @@ using namespace aurdf;
 extern "C" int aurdf_nn_l2(const void *query_xyz, const int32_t *query_off, const void *target_xyz,
                            const int32_t *target_off, int pts_dtype, int32_t n_groups, int64_t n_queries,
                            int32_t *out_idx, double *out_d2, aurdf_stream_t stream_) {
+    aurdf::NvtxRange nvtx_range("aurdf_nn_l2");
     cudaStream_t stream = (cudaStream_t)stream_;
     AURDF_REQUIRE(n_groups >= 0 && n_queries >= 0, "aurdf_nn_l2: negative size");
     if (n_groups == 0 || n_queries == 0) return AURDF_OK;

@@ -117,6 +117,7 @@ using namespace aurdf;
 
 extern "C" int aurdf_se3_apply(const void *xyz, const int32_t *off, const void *T, int32_t n_groups,
                                int64_t n_points, int dtype, void *out_xyz, aurdf_stream_t stream_) {
+    aurdf::NvtxRange nvtx_range("aurdf_se3_apply");
     cudaStream_t stream = (cudaStream_t)stream_;
     AURDF_REQUIRE(n_groups >= 0 && n_points >= 0, "aurdf_se3_apply: negative size");
     if (n_groups == 0 || n_points == 0) return AURDF_OK;
@@ -134,6 +135,7 @@ extern "C" int aurdf_se3_apply(const void *xyz, const int32_t *off, const void *
 extern "C" int aurdf_se3_apply_bwd(const void *grad_out, const void *xyz, const int32_t *off, const void *T,
                                    int32_t n_groups, int64_t n_points, int dtype, void *grad_xyz, void *grad_T,
                                    aurdf_stream_t stream_) {
+    aurdf::NvtxRange nvtx_range("aurdf_se3_apply_bwd");
     cudaStream_t stream = (cudaStream_t)stream_;
     AURDF_REQUIRE(n_groups >= 0 && n_points >= 0, "aurdf_se3_apply_bwd: negative size");
     if (n_groups == 0) return AURDF_OK;
@@ -151,6 +153,7 @@ extern "C" int aurdf_se3_apply_bwd(const void *grad_out, const void *xyz, const 
 
 extern "C" int aurdf_se3_to_local(const double *xyz, const int32_t *off, const double *T, int32_t n_groups,
                                   int64_t n_points, double *out_xyz, aurdf_stream_t stream_) {
+    aurdf::NvtxRange nvtx_range("aurdf_se3_to_local");
     cudaStream_t stream = (cudaStream_t)stream_;
     AURDF_REQUIRE(n_groups >= 0 && n_points >= 0, "aurdf_se3_to_local: negative size");
     if (n_groups == 0 || n_points == 0) return AURDF_OK;
