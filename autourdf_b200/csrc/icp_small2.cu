@@ -343,7 +343,7 @@ icp_small2_kernel(const IcpParams p) {
                 if (r == 0) stamp(4);   // merge + certificate + exact distance done
                 // exact rescan of the uncertified points of this warp (~1e-3 of them; duplicates always):
                 // float64, the reference's operation order, strict '<' in ascending index order
-                if (__any_sync(0xffffffffu, need_exact)) {
+                if (__builtin_expect(__any_sync(0xffffffffu, need_exact) != 0, 0)) {
                     double bd = INFINITY;
                     int bj = -1;
                     if (need_exact) {
@@ -435,7 +435,7 @@ icp_small2_kernel(const IcpParams p) {
                     for (int cc = 0; cc < 3; ++cc) sigma[r][cc] = n * t[4 * (r + 1) + cc + 1] - t[4 * (r + 1)] * t[cc + 1];
                 stamp(20);   // totals loaded, covariance formed
                 {
-                    if (!kabsch_rotation_newton4(sigma, R)) {   // reflection / rank-deficient / large step: Jacobi SVD, warm-started
+                    if (__builtin_expect(!kabsch_rotation_newton4(sigma, R), 0)) {   // reflection / rank-deficient / large step: Jacobi SVD, warm-started
                         // (copies: the out-of-line call takes addresses, and sigma / R must stay in registers
                         // on the fast path)
                         double sg2[3][3], R2[3][3];
@@ -579,7 +579,7 @@ icp_small2_kernel(const IcpParams p) {
                         s_tot[lane] = v;
                     }
                     __syncwarp();
-                    if (s_strict) fit_strict();
+                    if (__builtin_expect(s_strict != 0, 0)) fit_strict();   // rare: kept off the hot instruction stream
                     else if (lane == 0) fit_fast();
                 }
             } else if (warp == conv_w) {

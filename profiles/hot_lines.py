@@ -1,11 +1,12 @@
 #!/usr/bin/env python
 """Aggregate the warp-stall samples and executed instructions of the kernel in an ncu report by SOURCE LINE
 (needs -lineinfo at compile time and --import-source on at capture time; runs here, no GPU).
-    python profiles/hot_lines.py <report.ncu-rep> [top]"""
+    python profiles/hot_lines.py <report.ncu-rep> [top] [kernel-name regex]"""
 import collections, csv, io, subprocess, sys
 
 rep, top = sys.argv[1], int(sys.argv[2]) if len(sys.argv) > 2 else 25
-raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass,cuda"], capture_output=True, text=True).stdout
+sel = ["--kernel-name", "regex:" + sys.argv[3]] if len(sys.argv) > 3 else []
+raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass,cuda"] + sel, capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
 h = next(i for i, r in enumerate(rows) if "# Samples" in r)
 hdr, data = rows[h], rows[h + 1:]
@@ -20,10 +21,21 @@ def num(v):
 
 
 agg = collections.defaultdict(lambda: [0, 0, 0, collections.Counter(), ""])
+cur_file = ""
+for r in rows[:h]:
+    if r and r[0] == "File Path":
+        cur_file = r[1].split("/")[-1]
+seen_fn = 0
 for r in data:
-    if len(r) <= ith:
+    if r and r[0] == "File Path":
+        cur_file = r[1].split("/")[-1]
         continue
-    a = agg[r[iline]]
+    if r and r[0] == "Function Name":
+        seen_fn += 1
+        continue
+    if len(r) <= ith or r[iline] == "Line No":
+        continue
+    a = agg[(cur_file + ":" + r[iline]) if r[iline].strip() else ""]
     a[0] += num(r[isamp]); a[1] += num(r[iex]); a[2] += num(r[ith]); a[4] = r[isrc]
     for i in stall:
         if r[i]:

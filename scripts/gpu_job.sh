@@ -1,2 +1,3 @@
-mkdir -p gpurun_out
-( timeout 600 python -m pytest tests/test_torch_ops_gpu.py tests/test_abi_cpu.py -x -q 2>&1 | tail -12 ) | tee gpurun_out/r02v_tests.log
+AURDF_BENCH_SKIP_CPU=1 timeout 200 python bench.py --steps 100 --warmup 5 2>/dev/null | tail -1 | python -c "
+import json,sys; d=json.loads(sys.stdin.read()); print('bench value', round(d['value']), 'e2e', round(d['e2e']['value']), 'kernel_ms', d['roofline']['kernel_ms'])"
+timeout 200 python scripts/tile_latency.py 2>&1 | grep -E "single tile max_iter=10000|all 900 tiles max_iter=10000|whole iteration|barrier A|totals"
