@@ -248,10 +248,15 @@ chamfer_fwd_kernel(const ChamferArgs a) {
     for (int k = 0; k < kChQPT; ++k) {
         const int lq = tid + k * kChThreads, i = qb * kCfQ + lq;
         if (i < pq) {
+            // eight slices per trip: the loads are independent, so their L2 latencies overlap (one at a time, the
+            // merge of ~30 slices was a third of the kernel at P = 5000)
             unsigned long long best = 0xffffffffffffffffULL;
-            for (int zz = 0; zz < a.nz[d]; ++zz) {
-                const unsigned long long v = __ldcg(gk + (size_t)zz * kCfQ + lq);
-                best = v < best ? v : best;
+            for (int z0 = 0; z0 < a.nz[d]; z0 += 8) {
+                unsigned long long v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) v[u] = z0 + u < a.nz[d] ? __ldcg(gk + (size_t)(z0 + u) * kCfQ + lq) : 0xffffffffffffffffULL;
+#pragma unroll
+                for (int u = 0; u < 8; ++u) best = v[u] < best ? v[u] : best;
             }
             a.idx[d][(size_t)n * pq + i] = (int)(best & 0xffffffffu);
             sum += __uint_as_float((unsigned)(best >> 32));
@@ -261,20 +266,32 @@ chamfer_fwd_kernel(const ChamferArgs a) {
     for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
     if (lane == 0) s_w[warp] = sum;
     __syncthreads();
-    if (tid == 0) {
-        float tot = 0.f;
-        for (int w = 0; w < kChThreads / 32; ++w) tot += s_w[w];
-        a.psum[(d ? a.groups[0] : 0) + grp] = tot;
-        *cnt = 0;                                  // ready for the next call
-        __threadfence();
-        const int total = a.groups[0] + a.groups[1];
-        if (atomicAdd(a.done, 1) == total - 1) {   // last query block of all: the loss, in a fixed order
+    if (warp == 0) {
+        float tot = lane < kChThreads / 32 ? s_w[lane] : 0.f;
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);   // fixed tree: deterministic
+        int last_of_all = 0;
+        if (lane == 0) {
+            a.psum[(d ? a.groups[0] : 0) + grp] = tot;
+            *cnt = 0;                                  // ready for the next call
+            __threadfence();
+            last_of_all = atomicAdd(a.done, 1) == a.groups[0] + a.groups[1] - 1;
+        }
+        last_of_all = __shfl_sync(0xffffffffu, last_of_all, 0);
+        if (last_of_all) {   // last query block of all: the loss, every lane a strided share, then a fixed tree
             __threadfence();
             float l0 = 0.f, l1 = 0.f;
-            for (int g = 0; g < a.groups[0]; ++g) l0 += __ldcg(a.psum + g);
-            for (int g = 0; g < a.groups[1]; ++g) l1 += __ldcg(a.psum + a.groups[0] + g);
-            *a.loss = l0 * a.w[0] + l1 * a.w[1];
-            *a.done = 0;
+            for (int g = lane; g < a.groups[0]; g += 32) l0 += __ldcg(a.psum + g);
+            for (int g = lane; g < a.groups[1]; g += 32) l1 += __ldcg(a.psum + a.groups[0] + g);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                l0 += __shfl_xor_sync(0xffffffffu, l0, o);
+                l1 += __shfl_xor_sync(0xffffffffu, l1, o);
+            }
+            if (lane == 0) {
+                *a.loss = l0 * a.w[0] + l1 * a.w[1];
+                *a.done = 0;
+            }
         }
     }
 }

@@ -1,3 +1,5 @@
-AURDF_BENCH_SKIP_CPU=1 timeout 200 python bench.py --steps 100 --warmup 5 2>/dev/null | tail -1 | python -c "
-import json,sys; d=json.loads(sys.stdin.read()); print('bench value', round(d['value']), 'e2e', round(d['e2e']['value']), 'kernel_ms', d['roofline']['kernel_ms'])"
-timeout 200 python scripts/tile_latency.py 2>&1 | grep -E "single tile max_iter=10000|all 900 tiles max_iter=10000|whole iteration|barrier A|totals"
+mkdir -p gpurun_out
+( timeout 600 python -m pytest tests/test_chamfer_gpu.py tests/test_torch_ops_gpu.py tests/test_integration_gpu.py -x -q -m gpu 2>&1 | tail -4 )
+timeout 600 python scripts/bench_chamfer.py r02 2>&1 | tail -6
+cp profiles/r02_chamfer.md gpurun_out/
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:'chamfer_fwd|chamfer_bwd' -s 8 -c 2 -f -o gpurun_out/r02_prof_chamfer python scripts/profile_chamfer.py > gpurun_out/r02_prof_chamfer.log 2>&1
