@@ -349,16 +349,24 @@ def test_grid_search_adversarial(oracle):
     dev = torch.device("cuda")
     t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
 
-    def run(names, th, extra=None, max_iter=60):
+    def run(names, th, extra=None, max_iter=60, hint=None):
         srcs = [cases[n][0] for n in names] + ([extra[0]] if extra else [])
         tgts = [cases[n][1] for n in names] + ([extra[1]] if extra else [])
         s_off = np.concatenate([[0], np.cumsum([s.shape[0] for s in srcs])]).astype(np.int32)
         t_off = np.concatenate([[0], np.cumsum([q.shape[0] for q in tgts])]).astype(np.int32)
         r = ci.icp_sweep(t(np.concatenate(srcs)), t(s_off), t(np.concatenate(tgts)), t(t_off),
                          t(np.arange(len(srcs), dtype=np.int32)), None, None, t(np.stack([np.eye(4)] * len(srcs))),
-                         max_src_per_tile=int(np.diff(s_off).max()), max_corr=th, max_iter=max_iter)
+                         max_src_per_tile=int(np.diff(s_off).max()) if hint is None else hint, max_corr=th, max_iter=max_iter)
         torch.cuda.synchronize()
         return r, s_off, srcs, tgts
+
+    # no size hint (max_src_per_tile = 0): the slice does not fit the shared memory sized for the default, so the
+    # point state lives in the workspace spill area (unsorted points, no cache) -- same answers
+    r, s_off, srcs, tgts = run(["sheet", "rod"], 1.0, max_iter=25, hint=0)
+    for n, name in enumerate(["sheet", "rod"]):
+        o = oracle.icp_p2p(srcs[n], tgts[n], 1.0, np.eye(4), max_iter=25, use_kdtree=True)
+        assert int(r.iters[n]) == o["iters"] and np.array_equal(r.corr.cpu().numpy()[s_off[n]:s_off[n + 1]], o["corr"]), name
+        assert np.abs(r.T[n].cpu().numpy() - o["T"]).max() <= 1e-5
 
     cases["far"] = (far[0], far[1], -1.0)
     r, s_off, srcs, tgts = run(["far", "sheet"], 1.0, max_iter=0)
