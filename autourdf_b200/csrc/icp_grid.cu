@@ -56,9 +56,8 @@ struct GridView {
     int Gx, Gy, Gz;
 };
 
-// Grid loads.  SH = true: explicit ld.shared (the staged copy).  A generic pointer that may point to either
-// space compiles to generic loads, which the hardware serves through the global-memory path's scoreboard even
-// when the address is in shared memory: measured ~10x the latency of LDS in the dependent walk of a scan.
+// Grid loads.  SH = true: explicit ld.shared on the staged copy (a pointer that may point to either space compiles to
+// generic LD instructions; the explicit form keeps the walk on the shared-memory pipe and its short scoreboard).
 template <bool SH>
 __device__ __forceinline__ int ld_end(const GridView &gv, int c) {
     if constexpr (SH) {
@@ -494,12 +493,10 @@ __device__ __forceinline__ void grid_tile(const IcpParams &p, const int b) {
         return __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
     };
 
-    // One correspondence pass, one thread per source point: move, cache test, block scan, certificate.  (A variant
-    // in which eight lanes share a query was measured slower: the walk is a chain of dependent loads, and 32
-    // independent chains per warp hide more of that latency than four.)
     // debug hook (scripts/grid_stats.py): [0] queries, [1] cache hits, [2] block scans, [3] candidates evaluated,
-    // [4] exact fallbacks, [5] scans of the whole grid
-    // dbg[15] selects what is recorded: 1 = counters (their atomics distort every timing), 2 = phase timers
+    // [4] exact fallbacks, [5] scans of the whole grid, [7] passes, [12] wait at barrier A, [13] fit + barrier B,
+    // [14] longest ICP loop of a CTA (cycles).  dbg[15] selects what is recorded: 1 = counters (their atomics
+    // distort every timing), 2 = timers
     unsigned long long *dbg = reinterpret_cast<unsigned long long *>(p.dbg_clock);
     unsigned long long *dbgc = dbg && dbg[15] == 1 ? dbg : nullptr;
     if (dbg && dbg[15] != 2) dbg = nullptr;   // from here on dbg = timers only
@@ -515,7 +512,8 @@ __device__ __forceinline__ void grid_tile(const IcpParams &p, const int b) {
             }
         return c;
     };
-    auto pass_simple = [&](bool apply, auto sh_tag) __attribute__((always_inline)) {
+    // One correspondence pass, one thread per source point: move, cache test, block walk, certificate, moments.
+    auto pass_walk = [&](bool apply, auto sh_tag) __attribute__((always_inline)) {
         constexpr bool SH = decltype(sh_tag)::value;
         double acc[16];
 #pragma unroll
@@ -637,8 +635,8 @@ __device__ __forceinline__ void grid_tile(const IcpParams &p, const int b) {
     };
 
     auto pass = [&](bool apply) __attribute__((always_inline)) {
-        if (grid_sh) pass_simple(apply, std::true_type{});
-        else pass_simple(apply, std::false_type{});
+        if (grid_sh) pass_walk(apply, std::true_type{});
+        else pass_walk(apply, std::false_type{});
     };
 
     auto totals = [&](int w) __attribute__((always_inline)) -> int {
@@ -794,6 +792,7 @@ __device__ __forceinline__ void grid_tile(const IcpParams &p, const int b) {
         const bool apply = it >= 0;
         if (apply && rank == 0 && warp == kGW - 1) compose_pose();   // uses s_U of this iteration; next write is after barrier A
         pass(apply);
+        if (dbg && tid == 0) atomicAdd(dbg + 7, 1ull);
         long long t_a = dbg ? clock64() : 0;
         __syncthreads();   // barrier A
         if (dbg && tid == 0) { const long long t = clock64(); atomicAdd(dbg + 12, (unsigned long long)(t - t_a)); t_a = t; }

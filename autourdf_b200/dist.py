@@ -55,6 +55,15 @@ def frame_partition(batch, world: int):
     return [(cuts[r], cuts[r + 1]) for r in range(world)]
 
 
+def frame_partition_interleaved(batch, world: int):
+    """Frames dealt round-robin: rank r owns the transitions r, r + world, r + 2 world, ...  ICP work per tile is its
+    iteration count, which drifts along a long chain of frames (late frames of the 40-transition C5 chains hold the
+    170-190-iteration tiles): contiguous blocks balanced by points then leave one rank with all the slow frames
+    (profiles/r02_scaling.md), a round-robin deal gives every rank a sample of the whole chain."""
+    _require_frame_major(batch)
+    return [np.arange(r, batch.n_frames, world, dtype=np.int64) for r in range(world)]
+
+
 def tile_partition(batch, world: int):
     """Contiguous tile ranges [b0, b1) per rank, balanced by the pair-evaluation estimate n_s * M of
     each tile.  Frames may be split between ranks (their clouds are then replicated): this is how one
@@ -74,14 +83,23 @@ def tile_partition(batch, world: int):
 
 def sharded_sweep(batch, run_local, group=None, device="cpu", by="frames"):
     """Run ``run_local(sub_batch) -> dict(T (b,4,4), fitness, rmse, iters)`` on this rank's
-    share and all-gather the per-tile results.  ``by="frames"``: contiguous frame blocks;
+    share and all-gather the per-tile results.  ``by="frames"``: contiguous frame blocks; ``by="frames_rr"``: frames
+    dealt round-robin (balances chains whose difficulty drifts);
     ``by="tiles"``: contiguous tile ranges with replicated target clouds (a single frame's K
     clusters over several GPUs).  Returns (gathered dict over ALL tiles in the original tile
     order, this rank's local result dict, this rank's (f0, f1) or (b0, b1))."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
-    assert by in ("frames", "tiles")
-    if by == "tiles":
+    assert by in ("frames", "tiles", "frames_rr")
+    order = None   # tile indices in gathered (rank-major) order, when that is not the original order
+    if by == "frames_rr":
+        parts = frame_partition_interleaved(batch, world)
+        sel = [np.nonzero(np.isin(batch.tile_frame, fr))[0] for fr in parts]
+        sub, _ = batch.frame_select(parts[rank])
+        counts = [int(t.size) for t in sel]
+        order = np.concatenate(sel) if sel else np.zeros(0, dtype=np.int64)
+        f0, f1 = (int(parts[rank][0]), int(parts[rank][-1]) + 1) if parts[rank].size else (0, 0)
+    elif by == "tiles":
         parts = tile_partition(batch, world)
         f0, f1 = parts[rank]
         sub = batch.tile_slice(f0, f1)
@@ -111,6 +129,10 @@ def sharded_sweep(batch, run_local, group=None, device="cpu", by="frames"):
     dist.all_gather_into_tensor(out, pay, group=group)
     out = out.cpu().numpy().reshape(world, width, 19)
     rows = np.concatenate([out[r, :counts[r]] for r in range(world)], axis=0)
+    if order is not None:   # back to the original tile order
+        inv = np.empty_like(rows)
+        inv[order] = rows
+        rows = inv
     return dict(T=rows[:, :16].reshape(-1, 4, 4).copy(), fitness=rows[:, 16].copy(), rmse=rows[:, 17].copy(),
                 iters=rows[:, 18].astype(np.int32)), local, (f0, f1)
 
@@ -130,7 +152,8 @@ def cuda_run_local(device=None, **kw):
 
 class ShardedSweep:
     """Device-resident sharding of ONE batch over the ranks of ``group`` (strong scaling: the total work
-    is fixed, every rank owns a contiguous frame block or tile range).  The partition, the upload of this
+    is fixed, every rank owns a contiguous frame block, a contiguous tile range, or -- ``by="frames_rr"`` -- every
+    world-th frame).  The partition, the upload of this
     rank's share and the plan (outputs + workspace) happen once; ``run()`` is then this rank's five kernel
     launches plus ONE ``all_gather_into_tensor`` of the fitted poses (tiles x 16 float64, padded to the
     widest share), all on the current stream with no host synchronisation.  Reference: the per-cluster
@@ -142,8 +165,15 @@ class ShardedSweep:
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.group, self.kw = group, sweep_kw
-        assert by in ("frames", "tiles")
-        if by == "tiles":
+        assert by in ("frames", "tiles", "frames_rr")
+        self.order = None
+        if by == "frames_rr":
+            self.parts = frame_partition_interleaved(batch, self.world)
+            sel = [np.nonzero(np.isin(batch.tile_frame, fr))[0] for fr in self.parts]
+            self.sub, _ = batch.frame_select(self.parts[self.rank])
+            self.counts = [int(t.size) for t in sel]
+            self.order = np.concatenate(sel)
+        elif by == "tiles":
             self.parts = tile_partition(batch, self.world)
             lo, hi = self.parts[self.rank]
             self.sub = batch.tile_slice(lo, hi)
@@ -183,4 +213,9 @@ class ShardedSweep:
     def poses(self):
         """(B,4,4) float64 numpy: the gathered poses in the original tile order"""
         g = self.gathered.cpu().numpy().reshape(self.world, self.width, 16)
-        return np.concatenate([g[r, :self.counts[r]] for r in range(self.world)], axis=0).reshape(-1, 4, 4)
+        rows = np.concatenate([g[r, :self.counts[r]] for r in range(self.world)], axis=0)
+        if self.order is not None:   # interleaved frames: back to the original tile order
+            inv = np.empty_like(rows)
+            inv[self.order] = rows
+            rows = inv
+        return rows.reshape(-1, 4, 4)

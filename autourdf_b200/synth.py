@@ -171,6 +171,25 @@ class SweepBatch:
                           dict(self.meta))
 
 
+    def frame_select(self, frames):
+        """sub-batch holding the given frame transitions (ascending list) and their tiles, plus the indices of
+        those tiles in this batch: the unit of interleaved (round-robin) frame sharding"""
+        frames = np.asarray(frames, dtype=np.int64)
+        assert frames.size == 0 or np.all(np.diff(frames) > 0)
+        keep = np.isin(self.tile_frame, frames)
+        tiles = np.nonzero(keep)[0]
+        z = np.zeros(1, dtype=np.int32)
+        if tiles.size == 0:
+            return SweepBatch(self.src[:0], z, self.tgt[:0], z.copy(), self.tile_frame[:0], self.box[:0], z.copy(),
+                              self.init_T[:0], 0, self.n_clusters, dict(self.meta)), tiles
+        remap = np.full(int(self.tgt_off.shape[0]) - 1, -1, dtype=np.int32)
+        remap[frames] = np.arange(frames.size, dtype=np.int32)
+        cat = lambda arr, off, idx: np.concatenate([arr[off[i]:off[i + 1]] for i in idx])
+        offs = lambda off, idx: np.concatenate([[0], np.cumsum([off[i + 1] - off[i] for i in idx])]).astype(np.int32)
+        return SweepBatch(cat(self.src, self.src_off, tiles), offs(self.src_off, tiles), cat(self.tgt, self.tgt_off, frames),
+                          offs(self.tgt_off, frames), remap[self.tile_frame[tiles]], cat(self.box, self.box_off, tiles),
+                          offs(self.box_off, tiles), self.init_T[tiles], int(frames.size), self.n_clusters, dict(self.meta)), tiles
+
     def tile_slice(self, b0, b1):
         """sub-batch holding tiles [b0, b1) and (a copy of) every frame they refer to: the unit of
         cluster-level sharding, where each GPU holds a replica of the frame's target cloud"""

@@ -136,7 +136,7 @@ def config_dict(b, name, scaling, world):
     return {"workload": name, "frames_per_step" + per: b.n_frames, "points_per_frame": b.meta["n_points"],
             "clusters": b.n_clusters, "tiles_per_step" + per: b.n_tiles,
             "l2": "flushed between steps (256 MiB write) on the GPU arm",
-            "parallelism": (f"one {name} batch sharded by frame blocks over {world} GPU(s)" if scaling == "strong" else
+            "parallelism": (f"one {name} batch sharded by frames (round-robin) over {world} GPU(s)" if scaling == "strong" else
                             f"every GPU sweeps one {name} batch ({world} GPU(s))") + ", one all-gather of poses"}
 
 
@@ -280,7 +280,7 @@ def main():
     sharded = None
     if strong:
         from autourdf_b200.dist import ShardedSweep
-        sharded = ShardedSweep(b_all, dev)
+        sharded = ShardedSweep(b_all, dev, by=os.environ.get("AURDF_BENCH_SHARD", "frames_rr"))
         b = sharded.sub
     else:
         b = b_all

@@ -29,8 +29,7 @@ print(f"queries {c[0]}, cache hits {c[1]} ({100*c[1]/max(c[0],1):.1f} %), block 
       f"candidates per scan {c[3]/max(c[2],1):.1f} (brute force: {nt.mean():.0f}), exact fallbacks {c[4]} ({100*c[4]/max(c[0],1):.3f} %), "
       f"whole-grid scans {c[5]} ({100*c[5]/max(c[2],1):.2f} %)")
 passes = max(c[7], 1)
-print(f"per pass (thread 0 of every CTA, cycles): move+cache test {c[8]/passes:.0f}, item generation {c[9]/passes:.0f}, item scan {c[10]/passes:.0f}, "
-      f"per-query finish {c[11]/passes:.0f}, wait at barrier A {c[12]/passes:.0f}, fit + barrier B {c[13]/passes:.0f}")
+print(f"per pass (thread 0 of every CTA, cycles): wait at barrier A {c[12]/passes:.0f}, fit + barrier B {c[13]/passes:.0f}")
 print(f"longest ICP loop of a CTA: {c[14]} cycles = {c[14]/max(int(it.max())+1,1):.0f} per pass if it is the {it.max()}-iteration tile")
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 plan = ci.IcpSweep(b.n_tiles, b.src.shape[0], r.needed_capacity() + 64, int(ns.max()))

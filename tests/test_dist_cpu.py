@@ -42,6 +42,10 @@ def _worker(rank, world, port, q):
         ok = ok and loct["T"].shape[0] == b1 - b0 and 0 < b1 - b0 < one.n_tiles
         allb, _, _ = sharded_sweep(b, run_local, device="cpu", by="tiles")
         ok = ok and np.array_equal(allb["T"], full["T"]) and np.array_equal(allb["fitness"], full["fitness"])
+        # frames dealt round-robin: gathered rows come back in the original tile order
+        allr, locr, _ = sharded_sweep(b, run_local, device="cpu", by="frames_rr")
+        ok = ok and np.array_equal(allr["T"], full["T"]) and np.array_equal(allr["iters"], full["iters"])
+        ok = ok and np.array_equal(allr["rmse"], full["rmse"]) and 0 < locr["T"].shape[0] < b.n_tiles
         q.put((rank, ok, (f0, f1), parts, int(local["T"].shape[0])))
     except Exception as e:  # surface the failure instead of letting the parent wait for the queue
         q.put((rank, False, repr(e), None, 0))
@@ -138,3 +142,26 @@ def test_single_process_share_accepts_tensors_and_rejects_unsorted_frames():
     b.tile_frame = b.tile_frame[::-1].copy()
     with pytest.raises(ValueError):
         frame_partition(b, 2)
+
+
+def test_frame_select_and_interleaved_partition():
+    """round-robin frame sharding: every frame on exactly one rank, frame_select carries exactly those frames
+    (re-indexed) and their tiles, and the sub-batch sweeps to the same poses as the whole batch"""
+    from autourdf_b200 import synth
+    from autourdf_b200.dist import frame_partition_interleaved
+    from oracle import icp_oracle as O
+    b = synth.make_config("wx200", n_frames=6)
+    parts = frame_partition_interleaved(b, 3)
+    assert sorted(np.concatenate(parts).tolist()) == list(range(b.n_frames))
+    full = O.masked_icp_sweep(b.src, b.src_off, b.tgt, b.tgt_off, b.tile_frame, b.box, b.box_off, b.init_T)
+    seen = np.zeros(b.n_tiles, dtype=bool)
+    for fr in parts:
+        sub, tiles = b.frame_select(fr)
+        assert sub.n_frames == fr.size and sub.n_tiles == tiles.size and not seen[tiles].any()
+        seen[tiles] = True
+        assert np.array_equal(np.unique(sub.tile_frame), np.arange(fr.size))
+        r = O.masked_icp_sweep(sub.src, sub.src_off, sub.tgt, sub.tgt_off, sub.tile_frame, sub.box, sub.box_off, sub.init_T)
+        assert np.array_equal(r["T"], full["T"][tiles]) and np.array_equal(r["iters"], full["iters"][tiles])
+    assert seen.all()
+    empty, t = b.frame_select([])
+    assert empty.n_tiles == 0 and t.size == 0
