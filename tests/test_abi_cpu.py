@@ -13,7 +13,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 @pytest.fixture(scope="module")
 def lib():
     import __graft_entry__ as g
-    if not os.path.exists(os.path.join(ROOT, "autourdf_b200", "libaurdf.so")):
+    if not (os.path.exists(os.path.join(ROOT, "autourdf_b200", "libaurdf.so")) and
+            os.path.exists(os.path.join(ROOT, "autourdf_b200", "libaurdf_torch.so"))):
         g.build()
     from autourdf_b200 import _lib
     return _lib

@@ -9,7 +9,11 @@ pytestmark = pytest.mark.gpu
 
 @pytest.fixture(scope="module")
 def ops():
+    import os
     from autourdf_b200 import torch_ops
+    if not os.path.exists(torch_ops._PATH):
+        import __graft_entry__ as g
+        g.build()
     return torch_ops.load()
 
 
