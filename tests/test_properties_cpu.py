@@ -372,3 +372,112 @@ def test_small2_home_slot_mapping_is_a_bijection():
                 left = ns - 128 * r - w
                 assert k == (0 if left <= 0 else min(32, (left + 3) >> 2))
                 assert (0 if left <= 0 else min(8, (left + 15) >> 4)) == (k + 3) // 4
+
+
+# ------------------------------------------------------------------ grid-pruned search of icp_grid_kernel (icp_grid.cu)
+def _grid_build(Q):
+    """build_grid of icp_grid.cu in numpy float32: origin = first target, about one target per cell by volume, at most
+    64 cells per axis and n_t cells; returns (f32 targets about the origin, cell of every target, g0, h, inv_h, G, amax)"""
+    f = (Q - Q[0]).astype(np.float32)
+    lo, hi = f.min(0), f.max(0)
+    e = (hi - lo).astype(np.float32)
+    emax, nt = np.float32(e.max()), Q.shape[0]
+    G, h = np.array([1, 1, 1]), np.float32(1.0)
+    if emax > 0:
+        fl = np.float32(1e-3) * emax
+        h = np.float32(np.cbrt(np.maximum(e[0], fl) * np.maximum(e[1], fl) * np.maximum(e[2], fl) / np.float32(nt)))
+        h = np.maximum(h, emax / np.float32(64.0))
+        while True:
+            G = np.clip((e / h).astype(np.int64) + 1, 1, 64)
+            if G.prod() <= nt:
+                break
+            h = np.float32(h * np.float32(1.1))
+    inv_h = np.float32(1.0) / h
+    cell = lambda v: np.clip(np.floor((v - lo) * inv_h).astype(np.int64), 0, G - 1)
+    return f, cell(f), lo, h, inv_h, G, np.float32(np.abs(f).max()), cell
+
+
+def _grid_query(p32, f, cells, lo, h, G, aq, cell, R=None):
+    """one query of pass_walk: the block (3x3x3 of the query's cell, widened to the cube of half-side R and then until
+    it holds the ball through the best target found), float32 best / second best, face distance, certificate.
+    Returns (winner index or -1, certified)"""
+    amag = np.float32(max(aq, np.abs(p32).max()))
+    dl = np.float32(4.0) * U32 * amag
+    eps = np.float32(2e-5) * h + np.float32(8.0) * U32 * amag
+    c = cell(p32)
+    bl, bh = np.maximum(c - 1, 0), np.minimum(c + 1, G - 1)
+
+    def widen(bl, bh, R):
+        nl, nh = cell(p32 - R), cell(p32 + R)
+        grew = bool((nl < bl).any() or (nh > bh).any())
+        return np.minimum(bl, nl), np.maximum(bh, nh), grew
+
+    if R is not None:
+        bl, bh, _ = widen(bl, bh, np.float32(R) + np.float32(64.0) * dl + eps)
+    ring = 1
+    while True:
+        inside = ((cells >= bl) & (cells <= bh)).all(1)
+        idx = np.nonzero(inside)[0]
+        d = ((p32 - f[idx]) ** 2)
+        d = (d[:, 2] + (d[:, 1] + d[:, 0])).astype(np.float32) if idx.size else np.zeros(0, np.float32)   # fmaf chain ~ float32 sum
+        whole = bool((bl == 0).all() and (bh == G - 1).all())
+        if whole:
+            break
+        if idx.size:
+            m1 = d.min()
+            bl, bh, grew = widen(bl, bh, np.sqrt(m1) * np.float32(1.01) + np.float32(64.0) * dl + eps)
+            if not grew:
+                break
+        else:
+            ring *= 2
+            bl, bh = np.maximum(bl - ring, 0), np.minimum(bh + ring, G - 1)
+    if idx.size == 0:
+        return -1, False
+    order = np.argsort(d, kind="stable")
+    m1, k1 = d[order[0]], idx[order[0]]
+    m2 = d[order[1]] if idx.size > 1 else np.float32(np.inf)
+    # face distance: nearest face of the block that is not a face of the grid, deflated by eps
+    fb = np.float32(np.inf)
+    for a in range(3):
+        if bl[a] > 0:
+            fb = min(fb, np.float32(p32[a] - (lo[a] + np.float32(bl[a]) * h)))
+        if bh[a] < G[a] - 1:
+            fb = min(fb, np.float32((lo[a] + np.float32(bh[a] + 1) * h) - p32[a]))
+    if np.isfinite(fb):
+        fb = max(np.float32(fb - eps), np.float32(0.0))
+    m2e = min(m2, np.float32(fb * fb))
+    with np.errstate(invalid="ignore", over="ignore"):
+        tau = np.float32(16.0) * (dl * np.sqrt(m2e) * np.float32(1.001) + dl * dl + U32 * m2e)
+        ok = (f.shape[0] == 1 and not np.isfinite(m2e)) or (np.isfinite(m2e) and m2e - m1 > np.float32(2.0) * tau)
+    return int(k1), bool(ok)
+
+
+@pytest.mark.parametrize("kind", ["random", "bisector", "duplicates", "outside"])
+def test_grid_search_certificate_is_sound(kind):
+    """numpy emulation of the grid search of icp_grid_kernel on adversarial tiles: whenever the float32 block scan +
+    face-distance certificate accepts a winner, it is the float64 brute-force argmin over ALL targets (the kernel
+    sends everything else to the exact float64 path); queries far outside the grid, on bisector planes, on
+    duplicated targets, with and without a radius from a previous winner"""
+    rng = np.random.default_rng({"random": 11, "bisector": 12, "duplicates": 13, "outside": 14}[kind])
+    checked = accepted = 0
+    for trial in range(40):
+        nt = int(rng.choice([2, 17, 64, 300, 900, 2500]))
+        P, Q = _tile(rng, "random" if kind == "outside" else kind, nt, 48)
+        if kind == "outside":
+            P = P + rng.normal(scale=3.0 * np.ptp(Q, axis=0).max(), size=3)        # the whole cluster away from the targets
+        f, cells, lo, h, inv_h, G, aq, cell = _grid_build(Q)
+        ex = _exact_argmin(P, Q)
+        for i in range(P.shape[0]):
+            p32 = (P[i] - Q[0]).astype(np.float32)
+            # half the queries carry the radius through a previous winner (a random target: any target is an upper bound)
+            R = None
+            if i % 2:
+                jprev = int(rng.integers(0, nt))
+                R = np.float32(np.sqrt(((P[i] - Q[jprev]) ** 2).sum()) * 1.01)
+            k1, ok = _grid_query(p32, f, cells, lo, h, G, aq, cell, R)
+            checked += 1
+            if ok:
+                accepted += 1
+                assert k1 == ex[i], f"{kind}: certified a wrong neighbour (trial {trial}, n_t {nt}, point {i}): {k1} vs {ex[i]}"
+    frac = accepted / checked
+    assert frac > (0.97 if kind in ("random", "outside") else 0.4), f"{kind}: only {frac:.3f} of the queries certified"
