@@ -56,8 +56,10 @@ struct GridView {
     int Gx, Gy, Gz;
 };
 
-// Grid loads.  SH = true: explicit ld.shared on the staged copy (a pointer that may point to either space compiles to
-// generic LD instructions; the explicit form keeps the walk on the shared-memory pipe and its short scoreboard).
+// Grid loads.  SH = true: explicit ld.shared on a staged copy; SH = false: through the generic pointers, which point
+// at the staged copies when there are any.  The explicit form measured the same (9.07 vs 9.24 ms on C5 16384x32,
+// profiles/r02_notes.md), so the kernel instantiates only the generic one and can stage targets and cell table
+// independently.
 template <bool SH>
 __device__ __forceinline__ int ld_end(const GridView &gv, int c) {
     if constexpr (SH) {
@@ -176,11 +178,23 @@ static __device__ __noinline__ void scan_block_exact(const GridView &gv, Block b
                 const int a = row + bk.lx;
                 int k = a > 0 ? gv.ends[a - 1] : 0;
                 const int e = gv.ends[row + bk.hx];
-                for (; k < e; ++k) {
-                    const int j = __float_as_int(gv.gs[k].w);
-                    const double dx = __dsub_rn(x, __ldg(qx + j)), dy = __dsub_rn(y, __ldg(qy + j)), dz = __dsub_rn(z, __ldg(qz + j));
-                    const double d = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
-                    if (d < bd || (d == bd && j < bj)) { bd = d; bj = j; }
+                // four candidates per trip: their twelve float64 loads (L2 latency each) are in flight together
+                for (; k < e; k += 4) {
+                    int j[4];
+                    double qx_[4], qy_[4], qz_[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) j[u] = k + u < e ? __float_as_int(gv.gs[k + u].w) : -1;
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int jj = max(j[u], 0);
+                        qx_[u] = __ldg(qx + jj); qy_[u] = __ldg(qy + jj); qz_[u] = __ldg(qz + jj);
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const double dx = __dsub_rn(x, qx_[u]), dy = __dsub_rn(y, qy_[u]), dz = __dsub_rn(z, qz_[u]);
+                        const double d = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+                        if (j[u] >= 0 && (d < bd || (d == bd && j[u] < bj))) { bd = d; bj = j[u]; }
+                    }
                 }
             }
         }
@@ -396,7 +410,6 @@ __device__ __forceinline__ void grid_tile(const IcpParams &p, const int b) {
     gv.ends = p.gends + q0 + 2 * (long long)b;
     gv.g0x = gv.g0y = gv.g0z = 0.f; gv.h = gv.inv_h = 1.f; gv.Gx = gv.Gy = gv.Gz = 1;
     gv.gs_s = gv.ends_s = 0;
-    bool grid_sh = false;   // the grid has been staged in shared memory
     float aq = 0.f;
     if (nt > 0) {
         const float *gp = p.gpar + 8 * (size_t)b;
@@ -408,17 +421,19 @@ __device__ __forceinline__ void grid_tile(const IcpParams &p, const int b) {
         // dependent, scattered loads, which shared memory serves at a fraction of the L1 latency and without the
         // one-line-per-lane gather cost
         const int ncells = gv.Gx * gv.Gy * gv.Gz;
-        const size_t need = (size_t)nt * sizeof(float4) + (size_t)ncells * sizeof(int);
-        if (need <= (size_t)p.grid_smem_bytes) {
-            float4 *sg = reinterpret_cast<float4 *>(skey + kGridSortMax);   // grid_pcap is a multiple of 4: 16-byte aligned
-            int *se = reinterpret_cast<int *>(sg + nt);
+        // sorted targets first (one load per candidate), then the cell table (two loads per row) if it still fits:
+        // 8192 x ~9700 tiles keep their 155 KB of targets in shared memory and read the 39 KB table through L1
+        size_t avail = (size_t)p.grid_smem_bytes;
+        float4 *sg = reinterpret_cast<float4 *>(skey + kGridSortMax);   // grid_pcap is a multiple of 4: 16-byte aligned
+        if ((size_t)nt * sizeof(float4) <= avail) {
             for (int k = tid; k < nt; k += kGT) sg[k] = gv.gs[k];
-            for (int c = tid; c < ncells; c += kGT) se[c] = gv.ends[c];
             gv.gs = sg;
-            gv.ends = se;
-            gv.gs_s = smem_u32(sg);
-            gv.ends_s = smem_u32(se);
-            grid_sh = true;
+            avail -= (size_t)nt * sizeof(float4);
+            int *se = reinterpret_cast<int *>(sg + nt);
+            if ((size_t)ncells * sizeof(int) <= avail) {
+                for (int c = tid; c < ncells; c += kGT) se[c] = gv.ends[c];
+                gv.ends = se;
+            }
         }
     }
 
@@ -635,8 +650,7 @@ __device__ __forceinline__ void grid_tile(const IcpParams &p, const int b) {
     };
 
     auto pass = [&](bool apply) __attribute__((always_inline)) {
-        if (grid_sh) pass_walk(apply, std::true_type{});
-        else pass_walk(apply, std::false_type{});
+        pass_walk(apply, std::false_type{});   // generic loads: the staged copies are reached through the same pointers
     };
 
     auto totals = [&](int w) __attribute__((always_inline)) -> int {
