@@ -13,8 +13,8 @@
 //                       every cell.
 //   icp_grid_kernel<CS> CS = 1: persistent 512-thread CTAs take the tiles the small-tile kernel leaves from a
 //                       queue; CS = 8: a thread-block cluster per tile, every CTA a slice of the source points.
-//                       The sorted targets and the cell table are staged in shared memory when they fit (explicit
-//                       ld.shared), the source points of a CTA are kept in Morton order of their cells so that a
+//                       The sorted targets and the cell table are staged in shared memory when they fit (targets
+//                       first), the source points of a CTA are kept in Morton order of their cells so that a
 //                       warp's queries walk overlapping blocks, one thread per source point.  A query scans a
 //                       block of cells: the 3x3x3 neighbourhood of its own cell, widened to the cube that holds
 //                       the ball through the previous winner.  The float32 scan keeps best and second best;
