@@ -577,6 +577,7 @@ struct IcpParams {
     int grid_cs;           // CTAs per tile of the grid kernel launched for this sweep (1 or 8)
     int grid_pcap;         // most source points one of its CTAs keeps in shared memory
     int grid_smem_bytes;   // shared memory of a CTA set aside for the tile's sorted targets + cell table
+    float grid_cell_scale; // cell size relative to the one-target-per-cell-by-volume rule
     float4 *gs;            // workspace: cell-sorted float32 targets (x, y, z about the tile origin, compacted index)
     int *gends;            // workspace: end offset of every grid cell, tile b at toff[b] + 2 b
     float *gpar;           // workspace: 8 floats per tile (grid origin, cell size, 1 / cell size, max |coordinate|, cells per axis)

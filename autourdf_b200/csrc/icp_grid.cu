@@ -274,7 +274,7 @@ static __device__ __noinline__ void build_grid(const IcpParams &p, int b, int nt
         float h = 1.f;
         if (emax > 0.f) {
             const float fl = 1e-3f * emax;
-            h = cbrtf(fmaxf(e[0], fl) * fmaxf(e[1], fl) * fmaxf(e[2], fl) / (float)nt);
+            h = p.grid_cell_scale * cbrtf(fmaxf(e[0], fl) * fmaxf(e[1], fl) * fmaxf(e[2], fl) / (float)nt);
             h = fmaxf(h, emax / 64.f);
             for (;;) {
                 for (int d = 0; d < 3; ++d) G[d] = min(max((int)(e[d] / h) + 1, 1), 64);

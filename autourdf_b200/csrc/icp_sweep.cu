@@ -875,8 +875,10 @@ int launch_icp_grid(const IcpParams &P, int n_tiles, cudaStream_t stream);
 //   AURDF_ICP_GRID         0: no grid-pruned search (non-small tiles scan every target); 1 (default): icp_grid_kernel
 //   AURDF_ICP_GRID_CS_NS   source points per tile above which the grid kernel runs as 8-CTA clusters
 //   AURDF_ICP_GRID_SMEM_KB shared memory per CTA for a tile's sorted targets + cell table (one-CTA variant)
+//   AURDF_ICP_GRID_CELL_SCALE cell size relative to the one-target-per-cell-by-volume rule
 struct Tuning {
     int small, minb, split, strict_nt, grid, grid_cs_ns, grid_smem_kb;
+    float grid_cell_scale;
 };
 static const Tuning &tuning() {
     static const Tuning t = [] {
@@ -892,6 +894,9 @@ static const Tuning &tuning() {
         v.grid = geti("AURDF_ICP_GRID", 1);
         v.grid_cs_ns = geti("AURDF_ICP_GRID_CS_NS", 1024);
         v.grid_smem_kb = geti("AURDF_ICP_GRID_SMEM_KB", 112);
+        const char *cs = getenv("AURDF_ICP_GRID_CELL_SCALE");
+        v.grid_cell_scale = cs ? (float)atof(cs) : 1.0f;
+        if (!(v.grid_cell_scale > 0.05f && v.grid_cell_scale < 50.f)) v.grid_cell_scale = 1.0f;
         return v;
     }();
     return t;
@@ -1021,6 +1026,7 @@ extern "C" int aurdf_icp_sweep(const void *src_xyz, int pts_dtype, const int32_t
     // tiles): whatever one CTA per SM leaves after the source-point state and the static arrays
     P.grid_smem_bytes = P.grid_cs == 1 ? tn.grid_smem_kb * 1024 : (227 - 4) * 1024 - P.grid_pcap * 48 - 2048 * 4;
     if (P.grid_smem_bytes < 0) P.grid_smem_bytes = 0;
+    P.grid_cell_scale = tn.grid_cell_scale;
     P.gs = (float4 *)(ws + L.gs); P.gends = (int *)(ws + L.gends); P.gpar = (float *)(ws + L.gpar);
     P.glist = (int *)(ws + L.glist);
     box_count_kernel<<<n_tiles, kIcpThreads, 0, stream>>>(box_xyz, box_dtype, box_off, tgt_xyz, pts_dtype, tgt_off,
